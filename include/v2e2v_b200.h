@@ -209,7 +209,9 @@ int v2e_events_to_voxel(const void* events, int events_f64, int64_t n_events,
 /* -- standalone voxel normalisation (utils/event_process.py:132-154 / 157-177) ---------------
  * In place on device f32 [n] (n = num_bins*H*W).  mode: 0 'std', 1 'maxmin'.
  * hot_pixel_thresh > 0 zeroes |v| > thresh first (20/num_bins torch variant, 25/num_bins numpy
- * variant).  workspace: >= 64 bytes device, zero-initialised, left zeroed. */
+ * variant).  workspace: >= V2E_NORMALIZE_WORKSPACE_BYTES of device scratch (no initialisation
+ * needed).  Sums are reduced in a fixed order: results are run-to-run deterministic. */
+#define V2E_NORMALIZE_WORKSPACE_BYTES 40960
 int v2e_voxel_normalize(float* voxel, int64_t n, int mode, float hot_pixel_thresh,
                         void* workspace, void* stream);
 

@@ -1,0 +1,229 @@
+"""`-m gpu` parity tests: the CUDA emulator vs the golden fixtures and vs the CPU oracle.
+
+Bar (BASELINE.json north_star): state planes, polarity/count maps and num_events BIT-EXACT;
+voxel grids within rtol 1e-5 (+atol 1e-6 for the cancellation in (v-mean)/std).
+All calls go through the public EventEmulator -> v2e2v::emulate_pack -> C ABI.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import OracleEmulator
+from tests import gpu_common as gc
+from tests.golden.cases import CASES
+from tests.golden_io import GoldenCase, scalars_equal
+
+pytestmark = pytest.mark.gpu
+
+VOX_RTOL, VOX_ATOL = 1e-5, 1e-6
+
+
+def _to_cuda_frames(frames_u8, dtype=torch.float32):
+    return torch.from_numpy(frames_u8.astype(np.float32)).to("cuda").to(dtype)[None]
+
+
+@pytest.mark.parametrize("engine", gc.ENGINES)
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_reference_outputs(name, engine):
+    """CUDA path vs outputs of the unmodified reference (tests/golden)."""
+    g = GoldenCase(name)
+    em = gc.cuda_emulator(g.emu, engine)
+    pos, neg, nra = g.planes()
+    shp = (g.H, g.W)
+    em.set_planes(pos.reshape(shp), neg.reshape(shp), None if nra is None else nra.reshape(shp))
+    for k in range(g.packs):
+        frames, t_frames, lk, sh, sc = g.pack_inputs(k)
+        if lk is not None:
+            em.inject_leak_randn = torch.from_numpy(lk)
+        if sh is not None:
+            em.inject_shot_rand = torch.from_numpy(sh)
+        ev, nev = em(_to_cuda_frames(frames), t_frames)
+        assert scalars_equal(em._scalars, sc), "host scalar tables differ from the golden run"
+        want = g.pack_outputs(k)
+        assert nev == want["num_events"], f"pack {k}"
+        got = dict(base=em.base_log_frame, lp=em.lp_log_frame0, tmem=em.timestamp_mem)
+        for key in ("base", "lp", "tmem"):
+            if key == "lp" and g.emu["cutoff_hz"] <= 0:
+                continue
+            np.testing.assert_array_equal(got[key].cpu().numpy().reshape(-1), want[key],
+                                          err_msg=f"{key} pack {k}")
+        if g.raw:
+            np.testing.assert_array_equal(ev.cpu().numpy(), want["events"])
+        else:
+            np.testing.assert_allclose(ev.cpu().numpy().reshape(g.emu["num_bins"], -1),
+                                       want["voxel"], rtol=VOX_RTOL, atol=VOX_ATOL)
+
+
+@pytest.mark.parametrize("engine", gc.ENGINES)
+@pytest.mark.parametrize("cfg,H,W,fdt", [
+    (gc.CFG2, 180, 240, torch.float32),      # BASELINE configs[1]
+    (gc.CFG1, 180, 240, torch.float32),      # BASELINE configs[0] parameters
+    (gc.CFG2, 260, 346, torch.uint8),        # configs[3] geometry (W % 4 != 0), u8 ingest
+    (gc.CFG2, 50, 70, torch.bfloat16),
+])
+def test_vs_oracle_injected_noise(engine, cfg, H, W, fdt):
+    """Multi-pack run with injected noise: states, maps and counts bit-exact vs the oracle."""
+    T, packs, imax = 10, 3, 24
+    pos, neg, nra = gc.make_planes(7, H, W, cfg)
+    em = gc.cuda_emulator(cfg, engine, debug_maps=True)
+    orc = OracleEmulator(**cfg, threads=0)
+    em.set_planes(pos, neg, nra)
+    orc.set_planes(pos, neg, nra)
+    for k, fr, tfr in gc.video(3, packs, T, H, W):
+        lk, sh = gc.noise_arrays(100 + k, T, H * W, imax, True, True)
+        em.inject_leak_randn, em.inject_shot_rand = torch.from_numpy(lk), torch.from_numpy(sh)
+        ev, nev = em(fr.to("cuda").to(fdt), tfr)
+        ov, onev = orc.forward(fr.numpy().astype(np.float32), tfr, leak_randn=lk, shot_rand=sh,
+                               debug=True)
+        assert nev == onev, f"pack {k}"
+        gc.assert_state_equal(em, orc, cfg["cutoff_hz"] > 0, f"pack {k}")
+        np.testing.assert_array_equal(em.last_debug["max_iters"].cpu().numpy()[1:],
+                                      orc.last["max_iters"][1:])
+        for key in ("pol", "cnt", "final"):
+            np.testing.assert_array_equal(em.last_debug[key].cpu().numpy(), orc.last[key],
+                                          err_msg=f"{key} map pack {k}")
+        np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+
+
+@pytest.mark.parametrize("engine", gc.ENGINES)
+@pytest.mark.parametrize("rounds", [7, 10])
+def test_philox_mode_is_consistent_with_oracle(engine, rounds):
+    """PHILOX mode: export the draws the kernel made, inject them into the oracle, and require
+    the same bit-exact states (the in-kernel RNG only decides *which* draws are made)."""
+    cfg, H, W, T = gc.CFG2, 96, 128, 10
+    pos, neg, nra = gc.make_planes(11, H, W, cfg)
+    em = gc.cuda_emulator(cfg, engine, noise_mode="philox", debug_maps=True,
+                          philox_rounds=rounds)
+    orc = OracleEmulator(**cfg, threads=0)
+    em.set_planes(pos, neg, nra)
+    orc.set_planes(pos, neg, nra)
+    zs = []
+    for k, fr, tfr in gc.video(5, 3, T, H, W):
+        ev, nev = em(fr.to("cuda"), tfr)
+        d = em.last_debug
+        lk = d["leak_randn"].cpu().numpy()
+        sh = gc.shot_rand_from_decisions(d["shot"].cpu().numpy(), d["pol"].cpu().numpy())
+        ov, onev = orc.forward(fr.numpy(), tfr, leak_randn=lk, shot_rand=sh)
+        assert nev == onev
+        gc.assert_state_equal(em, orc, True, f"pack {k}")
+        np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+        zs.append(lk)
+    z = np.concatenate(zs).ravel()
+    # ~330k normals: mean ~ N(0, 1/sqrt(n)), variance within a few percent
+    assert abs(z.mean()) < 0.01 and abs(z.var() - 1.0) < 0.02
+    assert abs((z ** 3).mean()) < 0.03 and abs((z ** 4).mean() - 3.0) < 0.1
+
+
+def test_engines_agree_philox():
+    """Same seed/offset => stepwise and persistent engines draw identical noise."""
+    cfg, H, W, T = gc.CFG2, 64, 96, 10
+    pos, neg, nra = gc.make_planes(13, H, W, cfg)
+    outs = []
+    for engine in gc.ENGINES:
+        torch.manual_seed(0)
+        em = gc.cuda_emulator(cfg, engine, noise_mode="philox")
+        em.philox_seed = 1234
+        em.set_planes(pos, neg, nra)
+        res = []
+        for k, fr, tfr in gc.video(9, 3, T, H, W):
+            ev, nev = em(fr.to("cuda"), tfr)
+            res.append((ev.cpu().numpy(), nev, em.base_log_frame.cpu().numpy().copy()))
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert a[1] == b[1]
+        np.testing.assert_array_equal(a[2], b[2])
+        np.testing.assert_allclose(a[0], b[0], rtol=VOX_RTOL, atol=VOX_ATOL)
+
+
+def test_shot_noise_rate_statistics():
+    """PHILOX shot events occur at ~(rate/2)*fac*(thr/nominal) per pixel-second on pixels with
+    a sub-threshold brightness change (emulator_utils.py:173-188).  A strip of strongly
+    flickering pixels keeps the per-frame iteration count > 0 (no iterations, no shot events:
+    v2e_model.py:449)."""
+    H, W, T = 128, 128, 10
+    cfg = dict(gc.CFG1, shot_noise_rate_hz=20.0, leak_rate_hz=0.0)
+    for engine in gc.ENGINES:
+        em = gc.cuda_emulator(cfg, engine, noise_mode="philox", debug_maps=True)
+        g = torch.Generator().manual_seed(0)
+        base = torch.randint(60, 200, (1, 1, H, W), generator=g).float()
+        total, frames_done = 0, 0
+        for k in range(20):
+            flick = torch.randint(0, 2, (1, T, H, W), generator=g).float() * 4 - 2
+            fr = (base + flick).round()
+            fr[:, 0::2, 0, :] = 10.0       # row 0 flips between 10 and 200 every frame
+            fr[:, 1::2, 0, :] = 200.0
+            ev, nev = em(fr.to("cuda"), gc.stamps(k, T, 1000.0))
+            fin = em.last_debug["final"].view(T - 1, H, W)
+            total += int(fin[:, 1:, :].sum().item())
+            frames_done += T - 1
+        rate = total / ((H - 1) * W * frames_done / 1000.0)
+        # intensity ~130 -> fac = 1 - 0.75*(150/275) = 0.59; thr/nominal ~ 1  => ~5.9 Hz
+        exp = 10.0 * (1 - 0.75 * ((130 + 20) / 275.0))
+        assert 0.8 * exp < rate < 1.2 * exp, (engine, rate, exp)
+
+
+def test_full_size_1280x720_properties():
+    """BASELINE configs[2] geometry: oracle parity of one steady-state pack + invariants."""
+    cfg, H, W, T = gc.CFG2, 720, 1280, 10
+    pos, neg, nra = gc.make_planes(17, H, W, cfg)
+    em = gc.cuda_emulator(cfg, "auto", noise_mode="philox", debug_maps=True)
+    orc = OracleEmulator(**cfg, threads=0)
+    em.set_planes(pos, neg, nra)
+    orc.set_planes(pos, neg, nra)
+    for k, fr, tfr in gc.video(21, 2, T, H, W):
+        em.debug_maps = True
+        ev, nev = em(fr.to("cuda"), tfr)
+        d = em.last_debug
+        # sum of final_evts_frame over pixels and frames == num_events (checksum of checksums)
+        assert int(d["final"].sum().item()) == nev
+        lk = d["leak_randn"].cpu().numpy()
+        sh = gc.shot_rand_from_decisions(d["shot"].cpu().numpy(), d["pol"].cpu().numpy())
+        ov, onev = orc.forward(fr.numpy(), tfr, leak_randn=lk, shot_rand=sh)
+        assert nev == onev
+        gc.assert_state_equal(em, orc, True, f"pack {k}")
+        np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+        # normalised grid: nonzeros have mean 0 / std 1
+        v = ev[ev != 0].double()
+        assert abs(v.mean().item()) < 1e-4 and abs(v.std(unbiased=False).item() - 1) < 1e-4
+
+
+def test_time_order_error_and_reset():
+    em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
+    fr = torch.randint(0, 255, (1, 4, 16, 16)).float().cuda()
+    t = torch.tensor([[0.0, 0.001, 0.002, 0.003]], dtype=torch.float64)
+    em(fr, t)
+    with pytest.raises(ValueError, match="must be later than previous"):
+        em(fr, t)
+    em.reset()
+    assert em.base_log_frame is None
+    v, n = em(fr, t)          # works again after reset
+    assert v.shape == (1, 5, 16, 16)
+
+
+def test_b_gt_1_rejected_and_cpu_tensor_rejected():
+    em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
+    t = torch.tensor([[0.0, 0.003]], dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        em(torch.zeros(2, 4, 16, 16, device="cuda"), t)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        em(torch.zeros(1, 4, 16, 16), t)
+
+
+def test_non_integer_frames_slow_path():
+    """Non-integer frame values take the fp64 lin_log path and still match the oracle."""
+    cfg = dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0)
+    H, W, T = 32, 48, 6
+    pos, neg, _ = gc.make_planes(5, H, W, cfg)
+    for engine in gc.ENGINES:
+        em = gc.cuda_emulator(cfg, engine)
+        orc = OracleEmulator(**cfg)
+        em.set_planes(pos, neg)
+        orc.set_planes(pos, neg)
+        g = torch.Generator().manual_seed(3)
+        for k in range(2):
+            fr = torch.rand(1, T, H, W, generator=g) * 255     # arbitrary float values
+            tfr = gc.stamps(k, T, 1000.0)
+            ev, nev = em(fr.cuda(), tfr)
+            ov, onev = orc.forward(fr.numpy(), tfr)
+            assert nev == onev
+            gc.assert_state_equal(em, orc, True)

@@ -1,0 +1,141 @@
+// v2e_api.cu — the extern "C" surface declared in include/v2e2v_b200.h.
+//
+// Validation, engine selection and error capture live here; the kernels are in
+// v2e_stepwise.cu, v2e_persistent.cu and v2e_voxel.cu.  No torch types, no allocation.
+#include "v2e_engine.cuh"
+
+namespace v2e {
+
+static std::atomic<long long> g_launches{0};
+static thread_local cudaError_t t_last_cuda = cudaSuccess;
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int cuda_ok(cudaError_t e) {
+    if (e == cudaSuccess) return V2E_OK;
+    t_last_cuda = e;
+    return V2E_ERR_CUDA;
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+static int make_cfg(const v2e_config* c, CfgDev& d) {
+    if (!c || c->abi_version != V2E_ABI_VERSION) return V2E_ERR_BAD_ARG;
+    if (c->height <= 0 || c->width <= 0 || c->num_bins < 1 || c->num_bins > V2E_MAX_BINS)
+        return V2E_ERR_BAD_ARG;
+    if ((long long)c->height * c->width > (1ll << 30)) return V2E_ERR_BAD_ARG;
+    if (c->frame_dtype < V2E_DT_F32 || c->frame_dtype > V2E_DT_BF16) return V2E_ERR_BAD_ARG;
+    if (c->voxel_dtype != V2E_DT_F32 && c->voxel_dtype != V2E_DT_BF16) return V2E_ERR_BAD_ARG;
+    if (c->output_mode < V2E_OUT_VOXEL || c->output_mode > V2E_OUT_VOXEL_UNNORM)
+        return V2E_ERR_BAD_ARG;
+    if (c->noise_mode < V2E_NOISE_OFF || c->noise_mode > V2E_NOISE_PHILOX) return V2E_ERR_BAD_ARG;
+    if (!c->lut) return V2E_ERR_BAD_ARG;
+    d.H = c->height;
+    d.W = c->width;
+    d.P = c->height * c->width;
+    d.nb = c->num_bins;
+    d.cutoff_on = c->cutoff_on != 0;
+    d.leak_on = c->leak_on != 0;
+    d.shot_on = c->shot_on != 0;
+    d.noise_mode = c->noise_mode;
+    d.output_mode = c->output_mode;
+    d.voxel_bf16 = c->voxel_dtype == V2E_DT_BF16;
+    d.leak_rate = c->leak_rate;
+    d.leak_jitter = c->leak_jitter;
+    d.rn_pos = c->rn_pos;
+    d.rn_neg = c->rn_neg;
+    d.shot_inten_m1 = c->shot_inten_m1;
+    d.lut = c->lut;
+    return V2E_OK;
+}
+
+static int check_pack(const CfgDev& cfg, const v2e_pack& p, int T) {
+    const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
+    const bool shot = cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF;
+    if (p.sc.num_frames != T) return V2E_ERR_UNSUPPORTED;  // one T per launch
+    if (!p.frames || !p.base_log_frame || !p.timestamp_mem || !p.pos_thres || !p.neg_thres ||
+        !p.num_events)
+        return V2E_ERR_BAD_ARG;
+    if (cfg.cutoff_on && !p.lp_log_frame0) return V2E_ERR_BAD_ARG;
+    if (leak && !p.noise_rate) return V2E_ERR_BAD_ARG;
+    if (cfg.output_mode == V2E_OUT_RAW) {
+        if (!p.raw_events || p.raw_capacity < 0) return V2E_ERR_BAD_ARG;
+    } else if (!p.voxel) {
+        return V2E_ERR_BAD_ARG;
+    }
+    if (cfg.noise_mode == V2E_NOISE_INJECTED) {
+        if (leak && !p.leak_randn) return V2E_ERR_BAD_ARG;
+        if (shot && (!p.shot_rand || p.shot_imax <= 0)) return V2E_ERR_BAD_ARG;
+    }
+    const void* planes[] = {p.frames, p.base_log_frame, p.lp_log_frame0, p.timestamp_mem,
+                            p.pos_thres, p.neg_thres, p.noise_rate, p.voxel};
+    for (const void* q : planes)
+        if (q && !aligned16(q)) return V2E_ERR_BAD_ARG;
+    return V2E_OK;
+}
+
+}  // namespace v2e
+
+using namespace v2e;
+
+extern "C" {
+
+int v2e_abi_version(void) { return V2E_ABI_VERSION; }
+
+const char* v2e_error_string(int code) {
+    switch (code) {
+        case V2E_OK: return "ok";
+        case V2E_ERR_BAD_ARG: return "bad argument (null / misaligned pointer or bad dims)";
+        case V2E_ERR_UNSUPPORTED: return "unsupported request";
+        case V2E_ERR_TIME_ORDER: return "frame time must be later than previous frame time";
+        case V2E_ERR_CUDA: return "CUDA error";
+        case V2E_ERR_WORKSPACE: return "workspace too small";
+        case V2E_ERR_NO_DEVICE: return "no sm_100 CUDA device";
+        default: return "unknown error";
+    }
+}
+
+int v2e_last_cuda_error(void) { return (int)t_last_cuda; }
+const char* v2e_last_cuda_error_string(void) { return cudaGetErrorString(t_last_cuda); }
+int64_t v2e_launch_count(void) { return (int64_t)g_launches.load(); }
+
+size_t v2e_workspace_bytes(const v2e_config* c, int n_seq) {
+    CfgDev cfg;
+    if (make_cfg(c, cfg) != V2E_OK || n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH) return 0;
+    return step_layout(cfg, n_seq).total;
+}
+
+int v2e_resolve_engine(const v2e_config* c, int n_seq) {
+    CfgDev cfg;
+    const int rc = make_cfg(c, cfg);
+    if (rc != V2E_OK) return rc;
+    if (n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH) return V2E_ERR_BAD_ARG;
+    if (c->engine == V2E_ENGINE_STEPWISE) return V2E_ENGINE_STEPWISE;
+    const int fits = persistent_fits(cfg, c->frame_dtype, n_seq);
+    if (fits < 0) return fits;
+    if (c->engine == V2E_ENGINE_PERSISTENT) return fits ? V2E_ENGINE_PERSISTENT : V2E_ERR_UNSUPPORTED;
+    return fits ? V2E_ENGINE_PERSISTENT : V2E_ENGINE_STEPWISE;
+}
+
+int v2e_pack_forward(const v2e_config* c, const v2e_pack* packs, int n_seq, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    CfgDev cfg;
+    int rc = make_cfg(c, cfg);
+    if (rc != V2E_OK) return rc;
+    if (!packs || n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH || !workspace) return V2E_ERR_BAD_ARG;
+    const int T = packs[0].sc.num_frames;
+    if (T < 2 || T > V2E_MAX_FRAMES) return V2E_ERR_BAD_ARG;
+    for (int s = 0; s < n_seq; ++s)
+        if ((rc = check_pack(cfg, packs[s], T)) != V2E_OK) return rc;
+    if (workspace_bytes < step_layout(cfg, n_seq).total) return V2E_ERR_WORKSPACE;
+    if (!aligned16(workspace)) return V2E_ERR_BAD_ARG;
+    const int rounds = c->philox_rounds == 7 ? 7 : 10;
+    const int engine = v2e_resolve_engine(c, n_seq);
+    if (engine < 0) return engine;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (engine == V2E_ENGINE_PERSISTENT)
+        return run_persistent(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
+    return run_stepwise(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
+}
+
+}  // extern "C"

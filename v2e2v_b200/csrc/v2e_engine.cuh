@@ -1,0 +1,89 @@
+// v2e_engine.cuh — host-side declarations shared by the engines and the C-ABI layer.
+#pragma once
+
+#include <atomic>
+#include <cstring>
+
+#include "v2e_device.cuh"
+
+namespace v2e {
+
+constexpr int kMaxPartials = 2048;
+
+// Per-sequence work area inside the caller's workspace.  Zero on entry, zero on exit.
+struct SeqWork {
+    int gmax[V2E_MAX_FRAMES];             // per-frame max event count (atomicMax)
+    unsigned arrive[V2E_MAX_FRAMES + 4];  // persistent engine: per-frame barrier arrivals
+    unsigned long long raw_count;         // raw mode: rows appended
+    unsigned long long nev;               // persistent engine: event counter
+    unsigned exit_count;                  // persistent engine: CTAs that left (last one cleans)
+    unsigned pad;
+    double partials[3 * kMaxPartials];    // per-CTA (sum, sum of squares, nnz)
+};
+using StepWork = SeqWork;
+
+struct StepLayout {
+    size_t work_off, vox_off, cntpol_off, total;
+    int n_partials;
+};
+
+inline StepLayout step_layout(const CfgDev& cfg, int n_seq) {
+    StepLayout l;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    l.work_off = 0;
+    l.vox_off = up(sizeof(SeqWork) * (size_t)n_seq);
+    l.cntpol_off = up(l.vox_off + (size_t)n_seq * cfg.nb * cfg.P * sizeof(float));
+    l.total = up(l.cntpol_off + (size_t)n_seq * cfg.P * sizeof(int));
+    const size_t N = (size_t)cfg.nb * cfg.P;
+    size_t np = (N + 256 * 16 - 1) / (256 * 16);
+    if (np < 1) np = 1;
+    if (np > (size_t)kMaxPartials) np = kMaxPartials;
+    l.n_partials = (int)np;
+    return l;
+}
+
+inline void fill_seq(SeqDev& d, const v2e_pack& p) {
+    d.frames = p.frames;
+    d.base = p.base_log_frame;
+    d.lp = p.lp_log_frame0;
+    d.tmem = p.timestamp_mem;
+    d.pos = p.pos_thres;
+    d.neg = p.neg_thres;
+    d.nra = p.noise_rate;
+    d.voxel = p.voxel;
+    d.raw_events = p.raw_events;
+    d.raw_capacity = p.raw_capacity;
+    d.num_events = (unsigned long long*)p.num_events;
+    d.max_iters = p.max_iters;
+    d.leak_randn = p.leak_randn;
+    d.shot_rand = p.shot_rand;
+    d.shot_imax = p.shot_imax;
+    d.dbg_shot_imax = p.dbg_shot_imax;
+    d.dbg_pol = p.dbg_pol;
+    d.dbg_cnt = p.dbg_cnt;
+    d.dbg_final = p.dbg_final;
+    d.dbg_leak_randn = p.dbg_leak_randn;
+    d.dbg_shot = p.dbg_shot;
+    d.philox_seed = p.philox_seed;
+    d.philox_offset = p.philox_offset;
+    d.Tr = p.sc.Tr;
+    d.duration = p.sc.duration;
+    d.bins_m1 = p.sc.bins_m1;
+    d.first_pack = p.sc.first_pack;
+    d.shot_f64_mask = p.sc.shot_f64_mask;
+    d.T = p.sc.num_frames;
+}
+
+// launch accounting + CUDA error capture (v2e_api.cu)
+void count_launch(int n = 1);
+int cuda_ok(cudaError_t e);
+
+// engines
+int run_stepwise(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs, int n_seq,
+                 void* workspace, cudaStream_t st);
+int run_persistent(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs,
+                   int n_seq, void* workspace, cudaStream_t st);
+// 1 if the persistent engine can hold n_seq sequences of this config on chip on this device
+int persistent_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
+
+}  // namespace v2e

@@ -1,0 +1,386 @@
+"""`EventEmulator`: drop-in for the reference DVS emulator, backed by the sm_100a kernels.
+
+Mirrors `v2e.v2e_model.EventEmulator` of lsying009/V2E2V (v2e/v2e_model.py:32-536): same
+constructor keywords, `forward(frames, t_frames) -> (events, num_events)`, `reset()`, and the
+state attributes other code reads (`base_log_frame`, `lp_log_frame0`, `timestamp_mem`,
+`pos_thres`, `neg_thres`, `noise_rate_array`, `t_previous`, `num_bins`, `output_mode`).
+
+What runs where
+  * per-sequence initialisation (`_init`, v2e_model.py:156-240): the random per-pixel thresholds
+    and noise-rate plane are drawn with the same torch calls, in the same order, as the
+    reference, so a given torch seed gives the same sensor.
+  * per-pack scalars (v2e_model.py:303-318): host, `host_scalars.pack_scalars`.
+  * everything per pixel (lin-log, low-pass, leak, thresholding, refractory, voxel binning,
+    normalisation): one call of `v2e_pack_forward` through the `v2e2v::emulate_pack` op.
+
+Differences from the reference, all documented in DESIGN.md:
+  * batch_size must be 1 (the reference's B>1 mixes sequences, SURVEY.md trap T1); use
+    `EventEmulatorBatch` for many independent sequences in one launch.
+  * the per-frame noise draws come from an in-kernel Philox generator (`noise_mode='philox'`),
+    not from torch's global generator; `noise_mode='injected'` consumes caller-supplied draws
+    and is bit-exact to the reference given the same draws.
+  * refractory_period_s == 0 is accepted (the reference crashes on the second pack, trap T2).
+"""
+from __future__ import annotations
+
+import logging
+import math
+import random
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi, ops
+from .host_scalars import TimeState, pack_scalars
+
+logger = logging.getLogger(__name__)
+
+_LUT_CACHE = {}
+
+
+def lin_log_lut(device) -> torch.Tensor:
+    """[2,256] f32: lin_log(v) (v2e/emulator_utils.py:13-37) and (v+20)/275 (:40-45), v=0..255.
+
+    Built once per device with the reference's own arithmetic: fp64 piecewise lin/log rounded to
+    1e-8, then cast to f32; f32 add and divide for the rescale.
+    """
+    key = str(device)
+    lut = _LUT_CACHE.get(key)
+    if lut is None:
+        v = torch.arange(256, dtype=torch.float32)
+        x = v.double()
+        f = (1. / 20) * math.log(20)
+        y = torch.where(x <= 20, x * f, torch.log(x))
+        y = torch.round(y * 1e8) / 1e8
+        lut = torch.stack([y.float(), (v + 20) / 275.]).contiguous().to(device)
+        _LUT_CACHE[key] = lut
+    return lut
+
+
+def draw_thresholds(nominal: torch.Tensor, coef_large, coef_small, sigma, H, W, device):
+    """Per-pixel contrast thresholds (v2e_model.py:183-198): N(pl*C, sigma) everywhere, pixels
+    at even row and even column re-drawn from N(ps*C, sigma), clamped to >= 0.01.  Uses the
+    global CPU generator with the same draw order as the reference."""
+    B = nominal.numel()
+    large = torch.stack([torch.normal(coef_large * nominal[i], sigma, size=[1, H, W],
+                                      dtype=torch.float32).to(device) for i in range(B)], 0)
+    small = torch.stack([torch.normal(coef_small * nominal[i], sigma, size=[1, H, W],
+                                      dtype=torch.float32).to(device) for i in range(B)], 0)
+    large[:, :, 0::2, 0::2] = small[:, :, 0::2, 0::2]
+    return torch.clamp(large, min=0.01).contiguous()
+
+
+class EventEmulator(nn.Module):
+    """compute events based on the input frame (B200 kernels; see module docstring)."""
+
+    def __init__(
+            self,
+            output_mode,
+            pl=1, ps=1, ql=1, qs=1,
+            num_bins=5,
+            pos_thres=0.2,
+            neg_thres=0.2,
+            sigma_thres=0.03,
+            cutoff_hz=0,
+            leak_rate_hz=0.1,
+            refractory_period_s=0,
+            shot_noise_rate_hz=0,
+            leak_jitter_fraction=0.1,
+            noise_rate_cov_decades=0.1,
+            seed=0,
+            show_dvs_model_state: str = None,
+            device="cuda",
+            # ---- extensions (keyword-only in spirit; defaults keep the reference behaviour) ----
+            noise_mode: Optional[str] = None,     # 'philox' | 'injected' | 'off'
+            engine: str = "auto",                 # 'auto' | 'persistent' | 'stepwise'
+            voxel_dtype: torch.dtype = torch.float32,
+            philox_rounds: int = 10,
+            normalize: bool = True,
+            raw_capacity: Optional[int] = None,
+            debug_maps: bool = False,
+            debug_shot_imax: int = 24):
+        super().__init__()
+        if output_mode not in ("raw", "voxel_grid"):
+            raise ValueError("output_mode must be 'raw' or 'voxel_grid'")
+        if show_dvs_model_state:
+            raise NotImplementedError(
+                "show_dvs_model_state needs a display (cv2.imshow); use debug_maps=True and read "
+                "`last_debug` instead")
+        if not (1 <= num_bins <= _cabi.MAX_BINS):
+            raise ValueError(f"num_bins must be in [1,{_cabi.MAX_BINS}]")
+        logger.info("ON/OFF log_e temporal contrast thresholds: {} / {} +/- {}".format(
+            pos_thres, neg_thres, sigma_thres))
+        self.base_log_frame = None
+        self.t_previous = None
+        self.lp_log_frame0 = None
+        self.device = device
+        self.output_mode = output_mode
+        self.num_bins = num_bins
+        self.ql, self.qs, self.cutoff_hz = ql, qs, cutoff_hz
+        self.pl, self.ps, self.sigma_thres = pl, ps, sigma_thres
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("v2e2v_b200.EventEmulator runs on a CUDA device only "
+                               "(no CPU fallback); got device=%r" % (device,))
+        f32 = torch.float32
+        self.pos_thres = torch.tensor(pos_thres, dtype=f32, device=dev)
+        self.neg_thres = torch.tensor(neg_thres, dtype=f32, device=dev)
+        self.pos_thres_nominal = torch.tensor(pos_thres, dtype=f32, device=dev)
+        self.neg_thres_nominal = torch.tensor(neg_thres, dtype=f32, device=dev)
+        self._pos_nominal_host = torch.tensor(pos_thres, dtype=f32)
+        self._neg_nominal_host = torch.tensor(neg_thres, dtype=f32)
+        self.leak_rate_hz = leak_rate_hz
+        self.refractory_period_s = torch.tensor(refractory_period_s, dtype=f32, device=dev)
+        self._refractory_host = float(torch.tensor(refractory_period_s, dtype=f32))
+        self.shot_noise_rate_hz = shot_noise_rate_hz
+        self.leak_jitter_fraction = leak_jitter_fraction
+        self.noise_rate_cov_decades = noise_rate_cov_decades
+        self.SHOT_NOISE_INTEN_FACTOR = 0.25
+        self.show_input = show_dvs_model_state
+        if seed != 0:
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            random.seed(seed)
+        self.num_events = 0
+        self.frame_counter = 0
+
+        noisy = leak_rate_hz > 0 or shot_noise_rate_hz > 0
+        if noise_mode is None:
+            noise_mode = "philox" if noisy else "off"
+        if noise_mode not in ("philox", "injected", "off"):
+            raise ValueError("noise_mode must be 'philox', 'injected' or 'off'")
+        if noise_mode == "off" and noisy:
+            raise ValueError("noise_mode='off' requires leak_rate_hz == shot_noise_rate_hz == 0")
+        self.noise_mode = noise_mode
+        self.engine = engine
+        self.voxel_dtype = voxel_dtype
+        self.philox_rounds = philox_rounds
+        self.normalize = normalize
+        self.raw_capacity = raw_capacity
+        self.debug_maps = debug_maps
+        self.debug_shot_imax = debug_shot_imax
+        self.last_debug = {}
+        self.noise_rate_array = None
+        self.timestamp_mem = None
+        # injected-noise inputs for the next forward() (noise_mode='injected')
+        self.inject_leak_randn = None
+        self.inject_shot_rand = None
+        self.philox_seed = (int(torch.initial_seed()) ^ 0x5851F42D4C957F2D) & (2 ** 64 - 1)
+        self._pack_counter = 0
+        self._t_prev = TimeState()
+        self._launch = None
+        self._launch_key = None
+        self._handle = None
+        self._workspace = None
+        self._dev = dev
+        self._scalars = _cabi.PackScalars()
+
+    # ------------------------------------------------------------------------------------------
+    def _init(self, height, width):
+        """Per-sequence state (v2e_model.py:156-240).  base/lp/timestamp_mem are filled by the
+        kernel on the first pack (base = lp = lin_log(frame 0), timestamp_mem = -Tr)."""
+        dev = self._dev
+        shape = (1, 1, height, width)
+        self.base_log_frame = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.lp_log_frame0 = torch.empty(shape, dtype=torch.float32, device=dev)
+        self.pos_thres_real_nominal = self.pos_thres_nominal * torch.ones(1, device=dev)
+        self.neg_thres_real_nominal = self.neg_thres_nominal * torch.ones(1, device=dev)
+        if self.sigma_thres > 0:
+            self.pos_thres = draw_thresholds(self._pos_nominal_host.reshape(1), self.pl, self.ps,
+                                             self.sigma_thres, height, width, dev)
+            self.neg_thres = draw_thresholds(self._neg_nominal_host.reshape(1), self.pl, self.ps,
+                                             self.sigma_thres, height, width, dev)
+        else:
+            # the reference crashes for sigma_thres == 0 (trap T2); use the nominal thresholds
+            pos = torch.full(shape, float(self.pl * self._pos_nominal_host), device=dev)
+            pos[:, :, 0::2, 0::2] = float(self.ps * self._pos_nominal_host)
+            neg = torch.full(shape, float(self.pl * self._neg_nominal_host), device=dev)
+            neg[:, :, 0::2, 0::2] = float(self.ps * self._neg_nominal_host)
+            self.pos_thres = torch.clamp(pos, min=0.01)
+            self.neg_thres = torch.clamp(neg, min=0.01)
+        # shot-noise pre-probabilities (v2e_model.py:217-218) are recomputed in-kernel
+        if self.leak_rate_hz > 0:
+            z = torch.randn(shape, dtype=torch.float32, device=dev)
+            self.noise_rate_array = torch.exp(math.log(10) * self.noise_rate_cov_decades * z)
+        self.timestamp_mem = torch.empty(shape, dtype=torch.float32, device=dev)
+
+    def set_planes(self, pos_thres, neg_thres, noise_rate_array=None):
+        """Install externally generated per-pixel planes (tests, checkpointed sensors)."""
+        dev = self._dev
+
+        def prep(a):
+            t = torch.as_tensor(a, dtype=torch.float32).to(dev)
+            return t.reshape(1, 1, *t.shape[-2:]).contiguous()
+        self.pos_thres, self.neg_thres = prep(pos_thres), prep(neg_thres)
+        if noise_rate_array is not None:
+            self.noise_rate_array = prep(noise_rate_array)
+        self._planes_external = True
+
+    def reset(self):
+        """resets so that next use will reinitialize the base frame (v2e_model.py:242-250)"""
+        self.num_events_total = 0
+        self.num_events_on = 0
+        self.num_events_off = 0
+        self.base_log_frame = None
+        self.lp_log_frame0 = None
+        self.frame_counter = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _config(self, H, W, frame_dtype) -> _cabi.Config:
+        cfg = _cabi.Config()
+        cfg.abi_version = _cabi.ABI_VERSION
+        cfg.height, cfg.width, cfg.num_bins = H, W, self.num_bins
+        cfg.cutoff_on = int(self.cutoff_hz > 0)
+        cfg.leak_on = int(self.leak_rate_hz > 0)
+        cfg.shot_on = int(self.shot_noise_rate_hz > 0)
+        cfg.noise_mode = {"off": _cabi.NOISE_OFF, "injected": _cabi.NOISE_INJECTED,
+                          "philox": _cabi.NOISE_PHILOX}[self.noise_mode]
+        cfg.frame_dtype = ops._FRAME_DT[frame_dtype]
+        cfg.voxel_dtype = ops._VOX_DT[self.voxel_dtype]
+        if self.output_mode == "raw":
+            cfg.output_mode = _cabi.OUT_RAW
+        else:
+            cfg.output_mode = _cabi.OUT_VOXEL if self.normalize else _cabi.OUT_VOXEL_UNNORM
+        cfg.engine = {"auto": _cabi.ENGINE_AUTO, "stepwise": _cabi.ENGINE_STEPWISE,
+                      "persistent": _cabi.ENGINE_PERSISTENT}[self.engine]
+        f32 = torch.float32
+        cfg.leak_rate = float(torch.tensor(self.leak_rate_hz, dtype=f32))
+        cfg.leak_jitter = float(torch.tensor(self.leak_jitter_fraction, dtype=f32))
+        cfg.rn_pos = float(1. / self._pos_nominal_host.reshape(1))   # reciprocal()*1.
+        cfg.rn_neg = float(1. / self._neg_nominal_host.reshape(1))
+        cfg.shot_inten_m1 = float(torch.tensor(self.SHOT_NOISE_INTEN_FACTOR - 1, dtype=f32))
+        cfg.philox_rounds = self.philox_rounds
+        self._lut = lin_log_lut(self._dev)
+        cfg.lut = self._lut.data_ptr()
+        return cfg
+
+    def _get_launch(self, H, W, frame_dtype) -> ops.PackLaunch:
+        key = (H, W, frame_dtype)
+        if self._launch_key != key:
+            if self._handle is not None:
+                ops.release_launch(self._handle)
+            self._launch = ops.PackLaunch(self._config(H, W, frame_dtype), 1)
+            self._handle = ops.register_launch(self._launch)
+            self._launch_key = key
+            self._workspace = torch.zeros(self._launch.workspace_bytes, dtype=torch.uint8,
+                                          device=self._dev)
+        return self._launch
+
+    @property
+    def resolved_engine(self) -> Optional[str]:
+        if self._launch is None:
+            return None
+        return {_cabi.ENGINE_STEPWISE: "stepwise",
+                _cabi.ENGINE_PERSISTENT: "persistent"}.get(self._launch.resolve_engine())
+
+    def forward(self, frames, t_frames):
+        """Compute events based on a sequence of frames (v2e_model.py:290-536).
+
+        frames: [1, num_frames, H, W] on the CUDA device; float32 (the reference contract),
+            uint8 or bfloat16 (lossless for the integer-valued 0..255 frames every reference
+            reader produces).
+        t_frames: [1, 2] or [1, num_frames] float seconds.
+        Returns (events, num_events): events is the normalised voxel grid [1, num_bins, H, W]
+        or raw rows [N, 5] = [t, x, y, polarity, batch]; num_events is a python int.
+        """
+        if frames.dim() != 4:
+            raise ValueError("frames must be [batch_size=1, num_frames, height, width]")
+        batch_size, num_frames, height, width = frames.size()
+        if batch_size != 1:
+            raise NotImplementedError(
+                "batch_size must be 1 per EventEmulator (the reference mixes sequences for "
+                "B>1); use EventEmulatorBatch for independent sequences")
+        if not frames.is_cuda:
+            raise RuntimeError("frames must be on the CUDA device (no CPU fallback)")
+        if frames.dtype not in ops._FRAME_DT:
+            frames = frames.float()
+        frames = frames.contiguous()
+        if not (2 <= num_frames <= _cabi.MAX_FRAMES):
+            raise ValueError(f"num_frames must be in [2,{_cabi.MAX_FRAMES}]")
+        self.frame_counter += num_frames
+        first = self.base_log_frame is None
+        if first:
+            ext = getattr(self, "_planes_external", False)
+            keep = (self.pos_thres, self.neg_thres, self.noise_rate_array) if ext else None
+            self._init(height, width)
+            if ext:
+                self.pos_thres, self.neg_thres, self.noise_rate_array = keep
+        # per-pack scalars on the host; raises ValueError on non-increasing time (:335)
+        sc = pack_scalars(t_frames, num_frames, self.num_bins, self._refractory_host,
+                          self.cutoff_hz, self.ql, self.qs, self.shot_noise_rate_hz,
+                          self._t_prev, first, out=self._scalars)
+        self.t_previous = self._t_prev.value
+
+        pl = self._get_launch(height, width, frames.dtype)
+        pk = pl.packs[0]
+        P = height * width
+        dev = self._dev
+        pk.sc = sc
+        pk.frames = frames.data_ptr()
+        pk.base_log_frame = self.base_log_frame.data_ptr()
+        pk.lp_log_frame0 = self.lp_log_frame0.data_ptr()
+        pk.timestamp_mem = self.timestamp_mem.data_ptr()
+        pk.pos_thres = self.pos_thres.data_ptr()
+        pk.neg_thres = self.neg_thres.data_ptr()
+        pk.noise_rate = ops._ptr(self.noise_rate_array)
+        num_events = torch.empty(1, dtype=torch.int64, device=dev)
+        pk.num_events = num_events.data_ptr()
+        keep = [frames]
+        if self.output_mode == "raw":
+            cap = self.raw_capacity or 4 * P * (num_frames - 1)
+            out = torch.empty((cap, 5), dtype=torch.float32, device=dev)
+            pk.raw_events, pk.raw_capacity, pk.voxel = out.data_ptr(), cap, None
+        else:
+            out = torch.empty((1, self.num_bins, height, width), dtype=self.voxel_dtype,
+                              device=dev)
+            pk.voxel, pk.raw_events, pk.raw_capacity = out.data_ptr(), None, 0
+        if self.noise_mode == "injected":
+            if self.leak_rate_hz > 0:
+                lk = self.inject_leak_randn.to(dev, torch.float32).reshape(num_frames - 1, P)
+                lk = lk.contiguous()
+                pk.leak_randn = lk.data_ptr()
+                keep.append(lk)
+            if self.shot_noise_rate_hz > 0:
+                sh = self.inject_shot_rand.to(dev, torch.float32).reshape(num_frames - 1, -1, P)
+                sh = sh.contiguous()
+                pk.shot_rand, pk.shot_imax = sh.data_ptr(), sh.size(1)
+                keep.append(sh)
+        pk.philox_seed = self.philox_seed
+        pk.philox_offset = self._pack_counter
+        self._pack_counter += 1
+        mx = torch.zeros(num_frames, dtype=torch.int32, device=dev)
+        pk.max_iters = mx.data_ptr()
+        dbg = {}
+        if self.debug_maps:
+            dbg = dict(pol=torch.zeros((num_frames - 1, P), dtype=torch.int8, device=dev),
+                       cnt=torch.zeros((num_frames - 1, P), dtype=torch.int32, device=dev),
+                       final=torch.zeros((num_frames - 1, P), dtype=torch.int32, device=dev))
+            pk.dbg_pol, pk.dbg_cnt = dbg["pol"].data_ptr(), dbg["cnt"].data_ptr()
+            pk.dbg_final = dbg["final"].data_ptr()
+            if self.noise_mode == "philox":
+                imax = self.debug_shot_imax
+                dbg["leak_randn"] = torch.zeros((num_frames - 1, P), device=dev)
+                dbg["shot"] = torch.zeros((num_frames - 1, imax, P), dtype=torch.uint8, device=dev)
+                pk.dbg_leak_randn = dbg["leak_randn"].data_ptr()
+                pk.dbg_shot, pk.dbg_shot_imax = dbg["shot"].data_ptr(), imax
+        else:
+            pk.dbg_pol = pk.dbg_cnt = pk.dbg_final = pk.dbg_leak_randn = pk.dbg_shot = None
+
+        ops.emulate_pack(self._handle, frames, self.base_log_frame, self.lp_log_frame0,
+                         self.timestamp_mem, out, num_events, self._workspace)
+
+        self.last_debug = dict(max_iters=mx, **dbg)
+        n = int(num_events.item())          # python int, like the reference (forces a sync)
+        self.num_events = n
+        if self.output_mode == "raw":
+            rows = out[:min(n, out.size(0))]
+            if rows.size(0) > 1:
+                # v2e_model.py:527-534: time order; ties are broken by pixel for determinism
+                # (t >= 0, so its bit pattern is monotone)
+                tbits = rows[:, 0].contiguous().view(torch.int32).to(torch.int64)
+                key = (tbits << 32) | (rows[:, 2] * width + rows[:, 1]).to(torch.int64)
+                rows = rows[torch.argsort(key)]
+            return rows, n
+        return out, n
