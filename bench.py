@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — V2E emulate+voxelize throughput on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+A *step* is one pack (num_pack_frames = 10 HFR frames) of every sequence a rank owns, through the
+fused emulate+voxelize+normalise path.  Metric: Gpixel-frames/s = sequences*H*W*T*steps / time,
+summed over ranks (weak scaling: each rank owns its own sequences; no collective on the data
+path).  One JSON line is printed by rank 0.
+
+  value     device-resident inputs (a ring of distinct packs larger than L2), timed with CUDA
+            events, barrier + synchronize on both sides, max over ranks.
+  e2e       same metric through the public EventEmulator.forward with frames in pinned HOST
+            memory: per step one H2D copy of the pack and a D2H read of num_events.
+  roofline  algorithmic bytes (92 B/pixel/pack) / mean kernel duration (CUDA
+            events around each launch) vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle port (oracle/v2e_oracle.c, OpenMP) on a bounded sample.
+
+--impl reference times the CPU port on the host cores (the reference itself is pure Python and
+cannot travel to the GPU box; BASELINE.md holds its measured numbers from the build container).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+T_FRAMES = 10
+FPS = 1000.0
+WORKLOADS = {
+    # name: (H, W, sequences per GPU, description)
+    "cfg3": (720, 1280, 1, "BASELINE configs[2]: synthetic 1280x720 HFR video @1000 fps, 10-frame "
+                           "packs, fused emulate+voxelize, sensing-diversity parameters"),
+    "cfg2": (180, 240, 1, "BASELINE configs[1]: sensing-diversity V2E 180x240 + 5-bin voxel grid"),
+    "cfg4": (260, 346, 8, "BASELINE configs[3]: 346x260 sequences sharded by sequence, 8 per GPU"),
+}
+EMU = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, sigma_thres=0.03,
+           refractory_period_s=0.001, leak_rate_hz=0.1, shot_noise_rate_hz=1,
+           pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)     # cfg2 params + model_v2e2v.py:56-57
+ALGO_BYTES_PER_PIXEL_PACK = 92      # 9 f32 frames + 5 f32 bins + 6 planes in + 3 planes out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:]) if v == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def synth_pack_device(gen, base, H, W, dtype=torch.float32):
+    """synth-walk-v1 on the device: integer-valued random-walk frames."""
+    fr = (base + torch.cumsum(torch.randn(1, T_FRAMES, H, W, device=base.device, generator=gen) * 6,
+                              dim=1)).clamp(0, 255).round()
+    fr[:, 0] = base[:, 0]
+    return fr.to(dtype).contiguous(), fr[:, -1:].clone()
+
+
+def stamps(k):
+    return torch.linspace(k * (T_FRAMES - 1) / FPS, (k + 1) * (T_FRAMES - 1) / FPS, T_FRAMES,
+                          dtype=torch.float64)[None]
+
+
+# -----------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    from v2e2v_b200 import EventEmulator, _cabi
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    H, W, S, desc = WORKLOADS[args.workload]
+    K, Wm = args.steps, max(args.warmup, 3)
+    ring = max(2, -(-160_000_000 // (H * W * T_FRAMES * 4 * S)))   # > L2 (126 MB) of inputs
+    ring = min(ring, 16)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    torch.manual_seed(rank)
+    ems, packs = [], []
+    for s in range(S):
+        em = EventEmulator(device=dev, noise_mode=args.noise, engine=args.engine,
+                           philox_rounds=args.philox_rounds, lazy_num_events=True, **EMU)
+        ems.append(em)
+        base = torch.rand(1, 1, H, W, device=dev, generator=gen) * 255
+        seqp = []
+        for _ in range(ring):
+            fr, base = synth_pack_device(gen, base, H, W)
+            seqp.append(fr)
+        packs.append(seqp)
+    pinned = [[p.cpu().pin_memory() for p in seqp] for seqp in packs]
+    lib = _cabi.lib()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    k = 0
+    for _ in range(Wm):
+        for s in range(S):
+            ems[s](packs[s][k % ring], stamps(k))
+        k += 1
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.v2e_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K * S)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    i = 0
+    for _ in range(K):
+        for s in range(S):
+            ev[i][0].record()
+            ems[s](packs[s][k % ring], stamps(k))
+            ev[i][1].record()
+            i += 1
+        k += 1
+    e1.record()
+    barrier()
+    launches = lib.v2e_launch_count() - launches0
+    ms_total = reduce_max(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    kern_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    kern_mean_ms = sum(kern_ms) / len(kern_ms)
+    pxf_step = S * H * W * T_FRAMES
+    value = world * pxf_step * K / (ms_total * 1e-3) / 1e9
+
+    # ---- end to end through the public API with host frames ("e2e") ------------------------------
+    copy_stream = torch.cuda.Stream(dev)
+    stage = [[torch.empty_like(packs[s][0]) for _ in range(2)] for s in range(S)]
+    ready = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
+    freed = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
+    nev_host = torch.zeros(S, dtype=torch.int64).pin_memory()
+    for em in ems:
+        em.reset()
+
+    def e2e_step(kk):
+        b = kk & 1
+        for s in range(S):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[s][b])
+                stage[s][b].copy_(pinned[s][kk % ring], non_blocking=True)     # H2D, pinned
+                ready[s][b].record(copy_stream)
+        for s in range(S):
+            torch.cuda.current_stream(dev).wait_event(ready[s][b])
+            _, n = ems[s](stage[s][b], stamps(kk))
+            freed[s][b].record()
+            nev_host[s:s + 1].copy_(n, non_blocking=True)                      # D2H result
+    for kk in range(Wm):
+        e2e_step(kk)
+    barrier()
+    t0 = time.perf_counter()
+    for kk in range(Wm, Wm + K):
+        e2e_step(kk)
+    torch.cuda.synchronize(dev)
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * pxf_step * K / e2e_s / 1e9
+    h2d = S * H * W * T_FRAMES * 4
+    d2h = S * 8
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    algo_bytes = ALGO_BYTES_PER_PIXEL_PACK * H * W          # one launch = one pack of one sequence
+    achieved = algo_bytes / (kern_mean_ms * 1e-3) / 1e9
+    out = {
+        "metric": "V2E+voxel Gpixel-frames/s", "value": round(value, 3), "unit": "Gpixel-frames/s",
+        "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_total / K, 5),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (synth-walk-v1 random-walk video, integer-valued f32 frames)",
+        "config": {"workload": f"{args.workload}: {desc}", "height": H, "width": W,
+                   "num_pack_frames": T_FRAMES, "fps": FPS, "sequences_per_gpu": S,
+                   "parallelism": f"{world} x independent sequence shard(s), no collective",
+                   "emulator": EMU, "noise_mode": args.noise, "philox_rounds": args.philox_rounds,
+                   "engine": ems[0].resolved_engine, "frame_dtype": "f32", "voxel_dtype": "f32",
+                   "l2_policy": f"inputs larger than L2: ring of {ring} distinct packs "
+                                f"({ring * pxf_step * 4 / 1e6:.0f} MB) per GPU"},
+        "e2e": {"value": round(e2e_value, 3), "unit": "Gpixel-frames/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "EventEmulator.forward on frames copied from pinned host memory each "
+                        "step (double-buffered), num_events read back each step"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None,
+                     "peak_source": peak_src, "kernel": "k_persistent" if
+                     ems[0].resolved_engine == "persistent" else "k_phase_a/k_phase_b",
+                     "algorithmic_bytes_per_launch": algo_bytes,
+                     "kernel_ms_mean": round(kern_mean_ms, 5),
+                     "kernel_ms_min": round(kern_ms[0], 5)},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_port(H, W, budget_s=args.cpu_budget)
+    print(json.dumps(out), flush=True)
+
+
+# -----------------------------------------------------------------------------------------------
+def cpu_port(H, W, budget_s=12.0, threads=0, steps=None, warmup=1):
+    """Time the CPU oracle port (all host threads) on a bounded sample of the workload."""
+    from oracle.oracle import OracleEmulator
+    from tests.gpu_common import make_planes
+    cores = os.cpu_count() or 1
+    nthreads = threads or cores
+    em = OracleEmulator(**EMU, threads=nthreads)
+    em.set_planes(*make_planes(3, H, W, EMU))
+    rng = np.random.Generator(np.random.PCG64(5))
+    P = H * W
+    base = rng.random((1, H, W), dtype=np.float32) * 255
+    imax = 24
+    lk = rng.standard_normal((T_FRAMES - 1, P), dtype=np.float32)
+    sh = rng.random((T_FRAMES - 1, imax, P), dtype=np.float32)
+
+    def pack():
+        nonlocal base
+        fr = np.clip(base + np.cumsum(rng.standard_normal((T_FRAMES, H, W), dtype=np.float32) * 6, 0),
+                     0, 255).round().astype(np.float32)
+        fr[0] = base[0]
+        base = fr[-1:].copy()
+        return fr
+    frames = [pack() for _ in range(3)]
+    k = 0
+    for _ in range(warmup):
+        em.forward(frames[k % 3], stamps(k), leak_randn=lk, shot_rand=sh)
+        k += 1
+    times = []
+    t_start = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        em.forward(frames[k % 3], stamps(k), leak_randn=lk, shot_rand=sh)
+        times.append(time.perf_counter() - t0)
+        k += 1
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.perf_counter() - t_start > budget_s or len(times) >= 200:
+            break
+    med = sorted(times)[len(times) // 2]
+    return {"value": round(P * T_FRAMES / med / 1e9, 5), "unit": "Gpixel-frames/s",
+            "cores": nthreads, "kind": "port",
+            "sample": f"{len(times)} steady-state packs of {H}x{W}x{T_FRAMES} through "
+                      f"oracle/v2e_oracle.c (OpenMP, {nthreads} threads, injected noise), median",
+            "ms_per_step": round(med * 1e3, 3)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    H, W, S, desc = WORKLOADS[args.workload]
+    K, Wm = args.steps, max(args.warmup, 1)
+    K = min(K, 40)
+    r = cpu_port(H, W, steps=K, warmup=Wm)
+    out = {
+        "impl": "reference", "metric": "V2E+voxel Gpixel-frames/s", "value": r["value"],
+        "unit": "Gpixel-frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (synth-walk-v1)",
+        "config": {"workload": f"{args.workload}: {desc}", "height": H, "width": W,
+                   "num_pack_frames": T_FRAMES, "fps": FPS, "emulator": EMU,
+                   "note": "CPU port of the reference algorithm (the reference is pure Python/"
+                           "torch and is absent on the GPU box; its measured CPU numbers are in "
+                           "BASELINE.md)"},
+        "cpu_baseline": r,
+        "e2e": {"value": r["value"], "unit": "Gpixel-frames/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--noise", default="philox", choices=["philox", "off"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "persistent", "stepwise"])
+    ap.add_argument("--philox-rounds", type=int, default=10)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.noise == "off":
+        EMU.update(leak_rate_hz=0, shot_noise_rate_hz=0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,7 +2,8 @@
 //
 // Bit-exactness contract (DESIGN.md "Numerics"): every f32 operation the reference
 // performs as a separate ATen op is one correctly-rounded instruction here (__fmul_rn /
-// __fadd_rn / __fdiv_rn are never contracted into FMAs, independent of --fmad).
+// __fadd_rn / __fdiv_rn are never contracted into FMAs, independent of --fmad).  Code that only
+// feeds the in-kernel RNG (PHILOX mode) is free to use FMAs and fast intrinsics.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -64,13 +65,21 @@ __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
-// lin_log for an arbitrary (non-integer) frame value: v2e/emulator_utils.py:13-37 in fp64.
-static __device__ __noinline__ float lin_log_slow(float xf) {
+// lin_log / rescale for an arbitrary (non-integer) frame value: v2e/emulator_utils.py:13-45.
+// Out of line: integer-valued frames (every reader of the reference produces them) never come
+// here.
+static __device__ __noinline__ float2 log_inten_slow(float xf) {
     const double x = (double)xf;
     const double f = (1. / 20.) * 2.995732273553991;  // (1./threshold)*math.log(threshold)
     double y = (x <= 20.) ? x * f : log(x);
     y = rint(y * 1e8) / 1e8;
-    return (float)y;
+    return make_float2((float)y, fdiv(fadd(xf, 20.f), 275.f));
+}
+
+// floor(ad/den) for ad >= den (the ~4 % of pixel-frames that cross a threshold).  Out of line to
+// keep the per-pixel fast path small.
+static __device__ __noinline__ int count_div(float ad, float den) {
+    return (int)floorf(fdiv(ad, den));
 }
 
 // LUT in shared memory: float2 {lin_log(v), (v+20)/275}.
@@ -83,21 +92,19 @@ __device__ __forceinline__ void load_lut(float2* s_lut, const float* __restrict_
 // functions' own outputs); anything else -> fp64 slow path.
 __device__ __forceinline__ void log_inten(const float2* s_lut, float x, float& L, float& I) {
     const int v = __float2int_rn(x);
-    if (__builtin_expect((float)v == x && (unsigned)v < 256u, 1)) {
-        const float2 e = s_lut[v];
-        L = e.x;
-        I = e.y;
-    } else {
-        L = lin_log_slow(x);
-        I = fdiv(fadd(x, 20.f), 275.f);
-    }
+    float2 e;
+    if (__builtin_expect((float)v == x && (unsigned)v < 256u, 1)) e = s_lut[v];
+    else e = log_inten_slow(x);
+    L = e.x;
+    I = e.y;
 }
 
-// ---- frame loads (4 consecutive pixels) -------------------------------------------------------
+// ---- frame loads --------------------------------------------------------------------------------
 template <int FDT>
 __device__ __forceinline__ float load_frame1(const void* __restrict__ f, long long idx) {
     if (FDT == V2E_DT_U8) return (float)__ldg((const unsigned char*)f + idx);
-    if (FDT == V2E_DT_BF16) return __bfloat162float(((const __nv_bfloat16*)f)[idx]);
+    if (FDT == V2E_DT_BF16)
+        return __uint_as_float(((unsigned)__ldg((const unsigned short*)f + idx)) << 16);
     return __ldg((const float*)f + idx);
 }
 
@@ -109,7 +116,7 @@ __device__ __forceinline__ float4 load_frame4(const void* __restrict__ f, long l
         return make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
     }
     if (FDT == V2E_DT_BF16) {
-        const uint2 v = __ldg((const uint2*)((const __nv_bfloat16*)f + idx));
+        const uint2 v = __ldg((const uint2*)((const unsigned short*)f + idx));
         return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
                            __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
     }
@@ -130,14 +137,16 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     return ctr;
 }
 
-// Noise for the 4-pixel group G of frame n (engine-independent: a pure function of
-// (seed, pack offset, n, G)).  z[4]: standard normals (Box-Muller on 16+16 bit uniforms),
-// u[4]: 32-bit uniforms as raw words.  `stream` selects independent draws (0: per-frame draw,
-// >= 1: follow-up shot draws of the rare path).
+// Noise words: a pure function of (seed, pack offset, frame n, index, stream), hence identical in
+// both engines.
+//   stream 0, index = 4-pixel group G: .x/.y -> leak normals of pixels (0,1)/(2,3) of the group,
+//                                      .z    -> one byte per pixel: first stage of the shot test
+//   stream 1.., index = pixel p:       .x    -> second-stage / follow-up shot uniforms (rare)
 template <int R>
 __device__ __forceinline__ uint4 noise_words(unsigned long long seed, unsigned long long offset,
-                                             unsigned n, unsigned G, unsigned stream) {
-    const uint4 ctr = make_uint4(G, n | (stream << 8), (unsigned)offset, (unsigned)(offset >> 32));
+                                             unsigned n, unsigned index, unsigned stream) {
+    const uint4 ctr =
+        make_uint4(index, n | (stream << 8), (unsigned)offset, (unsigned)(offset >> 32));
     const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
     return philox4x32<R>(ctr, key);
 }
@@ -146,15 +155,46 @@ __device__ __forceinline__ uint4 noise_words(unsigned long long seed, unsigned l
 __device__ __forceinline__ void box_muller16(unsigned w, float& z0, float& z1) {
     const float u1 = (float)((w & 0xffffu) + 1u) * (1.0f / 65536.0f);
     const float u2 = (float)(w >> 16) * (1.0f / 65536.0f);
-    const float r = sqrtf(-2.0f * __logf(u1));
+    // sqrt(-2 ln u1) = sqrt(-2 ln2 * log2(u1))
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);
     z0 = r * c;
     z1 = r * s;
 }
 
-__device__ __forceinline__ float u32_to_unit(unsigned w) {  // [0,1) with 24 significant bits
-    return (float)(w >> 8) * (1.0f / 16777216.0f);
+// ---- shot noise in PHILOX mode: distribution-equivalent skip-ahead ------------------------------
+// The reference draws one uniform per (pixel, iteration) and fires with probability p per
+// iteration (emulator_utils.py:173-205).  P(any of ni iterations fires) = 1-(1-p)^ni <= ni*p
+// = shot_c*fac*(thr/nominal), which does not depend on ni, so the "anything at all?" test can
+// run before the per-frame max is known.  One uniform u decides: u >= bound -> nothing (exact);
+// u < bound -> candidate, and the same u gives the first firing iteration by inverting the
+// geometric law (exact); later firings use fresh uniforms.
+__device__ __forceinline__ float shot_any_bound(const CfgDev& cfg, float shot_c32, float I,
+                                                float thr, float rn) {
+    const float fac = fmaf(cfg.shot_inten_m1, I, 1.0f);
+    return shot_c32 * fac * (rn * thr) * 1.0001f;  // +1e-4 relative slack over rounding
+}
+
+// First stage: u = (byte + u2)/256 with u2 drawn only if the byte alone cannot exclude u < bound.
+__device__ __forceinline__ bool shot_stage1(unsigned byte, float bound) {
+    return (float)byte < bound * 256.0f;  // byte/256 <= u, so byte/256 >= bound -> u >= bound
+}
+
+template <int R>
+static __device__ __noinline__ float shot_uniform(unsigned long long seed,
+                                                  unsigned long long offset, int n, int p,
+                                                  unsigned byte) {
+    const uint4 w = noise_words<R>(seed, offset, (unsigned)n, (unsigned)p, 1);
+    return ((float)byte + (float)w.x * (1.0f / 4294967296.0f)) * (1.0f / 256.0f);
+}
+
+// Geometric skip: index of the first success of iid Bernoulli(p) trials, from one uniform.
+static __device__ __noinline__ int geometric_skip(float u, float p) {
+    if (!(p > 0.f)) return 0x7fffffff;
+    if (p >= 1.f) return 0;
+    const double g = floor(log1p(-(double)u) / log1p(-(double)p));
+    return g > 2.0e9 ? 0x7fffffff : (int)g;
 }
 
 // ---- sensing-diversity pattern ------------------------------------------------------------------
@@ -165,11 +205,6 @@ __device__ __forceinline__ bool is_small_px(int p, int W) {
 }
 
 // ---- per-pixel phase A: low-pass, leak, diff, polarity, count ------------------------------------
-struct PixelA {
-    float diff;  // tolerance-masked diff (v2e_model.py:394-395)
-    int cnt;     // event_counts (v2e_model.py:404)
-};
-
 // lp update (emulator_utils.py:75-93).  s = +inf encodes eps = 1 (q <= 0 branch).
 __device__ __forceinline__ float lowpass(float lp, float L, float I, float s) {
     float eps = fmul(I, s);           // I > 0, s = +inf -> +inf -> clamped to 1
@@ -184,27 +219,36 @@ __device__ __forceinline__ float leak_sub(float base, float lk_nra, float jit, f
     return fsub(base, fmul(fmul(sdt, clr), pos));
 }
 
+// diff / polarity / threshold / count (v2e_model.py:375,394-404).
+//   pol in {-1,0,+1}; C = threshold of the polarity side (0 if pol == 0); cnt = event_counts.
+// floor(|diff|/(C+1e-9)) == 0  <=>  |diff| < C+1e-9 (exact: the quotient of two floats a < b is
+// at most 1-2^-24, which is representable), so the division is only evaluated on a crossing.
+struct PixelA {
+    float pol, C;
+    int cnt;
+};
 __device__ __forceinline__ PixelA diff_count(float nw, float base, float pos, float neg) {
     PixelA r;
-    float diff = fsub(nw, base);
-    if (!(fabsf(diff) > 1e-6f)) diff = 0.f;
-    r.diff = diff;
-    const float C = diff > 0.f ? pos : (diff < 0.f ? neg : 0.f);
-    const float den = fadd(C, 1e-9f);
+    const float diff = fsub(nw, base);
     const float ad = fabsf(diff);
-    // floor(ad/den) == 0  <=>  ad < den (exact), so divide only when needed
-    r.cnt = (ad >= den) ? (int)floorf(fdiv(ad, den)) : 0;
+    const bool live = ad > 1e-6f;  // tolerance mask (:394-395); NaN -> not live, like masked_fill
+    const bool up = diff > 0.f;
+    r.pol = live ? (up ? 1.f : -1.f) : 0.f;
+    r.C = live ? (up ? pos : neg) : 0.f;
+    const float den = fadd(r.C, 1e-9f);
+    r.cnt = 0;
+    if (__builtin_expect(live && ad >= den, 0)) r.cnt = count_div(ad, den);
     return r;
 }
 
-// ---- per-pixel phase B: the iteration loop (v2e_model.py:449-522) --------------------------------
-struct FrameGlobals {  // derived from the per-frame global max (v2e_model.py:405-417,469)
+// ---- per-frame globals (v2e_model.py:405-417,469) -----------------------------------------------
+struct FrameGlobals {
     int mx;
     float ts_step;
-    bool gate;
+    int gate;
+    int f64;
     double a64;
     float a32;
-    bool f64;
 };
 
 __device__ __forceinline__ FrameGlobals frame_globals(int mx, float duration, float Tr,
@@ -220,103 +264,62 @@ __device__ __forceinline__ FrameGlobals frame_globals(int mx, float duration, fl
     return g;
 }
 
-
-// Shot-noise thresholds of one pixel (emulator_utils.py:173-188), f32 or f64 per trap T5.
-struct ShotThr {
-    double on64, off64;
-    float on32, off32;
-    float p_on, p_off;  // per-iteration firing probabilities (PHILOX mode)
-};
-
-__device__ __forceinline__ ShotThr shot_thresholds(const CfgDev& cfg, const FrameGlobals& g,
-                                                   float I, float pos, float neg) {
-    ShotThr t;
-    const float fac = fadd(fmul(cfg.shot_inten_m1, I), 1.0f);
-    const float ppp = fmul(cfg.rn_pos, pos);
-    const float npp = fmul(cfg.rn_neg, neg);
-    if (g.f64) {
-        const double snf = __dmul_rn(g.a64, (double)fac);
-        t.on64 = __dsub_rn(1.0, __dmul_rn(snf, (double)ppp));
-        t.off64 = __dmul_rn(snf, (double)npp);
-        t.on32 = 2.f; t.off32 = -1.f;
-        t.p_on = (float)(snf * (double)ppp);
-        t.p_off = (float)t.off64;
-    } else {
-        const float snf = fmul(g.a32, fac);
-        t.on32 = fsub(1.0f, fmul(snf, ppp));
-        t.off32 = fmul(snf, npp);
-        t.on64 = 2.; t.off64 = -1.;
-        t.p_on = fmul(snf, ppp);
-        t.p_off = t.off32;
-    }
-    return t;
-}
-
-// Conservative bound on P(any shot event in this pixel-frame) = 1-(1-p)^ni <= ni*p
-// = shot_c*fac*ppp: independent of ni, so the candidate test runs before the global max is known.
-__device__ __forceinline__ float shot_any_bound(const CfgDev& cfg, float shot_c32, float I,
-                                                float thr, float rn) {
-    const float fac = fmaf(cfg.shot_inten_m1, I, 1.0f);
-    return shot_c32 * fac * (rn * thr) * 1.0001f;  // +1e-4 relative slack over rounding
-}
-
-// Geometric skip: index of the first success of iid Bernoulli(p) trials, from one uniform.
-__device__ __forceinline__ int geometric_skip(float u, float p) {
-    if (!(p > 0.f)) return 0x7fffffff;
-    if (p >= 1.f) return 0;
-    const double g = floor(log1p(-(double)u) / log1p(-(double)p));
-    return g > 2.0e9 ? 0x7fffffff : (int)g;
-}
-
-// The per-pixel iteration loop.  VoxAdd: void(int bin, float val); Emit: void(float ts, float pol).
+// ---- per-pixel phase B: the iteration loop (v2e_model.py:449-522) --------------------------------
+// VoxAdd: void(int bin, float val); Emit: void(float ts, float pol).
 // Returns final_evts_frame for this pixel (post-refractory event count incl. shot events).
-//   cnt/diff: phase-A results; tm: timestamp_mem (updated in place)
-//   shot_mode: 0 none, 1 injected (reads sq.shot_rand), 2 philox (first_shot = first shot
-//   iteration index or INT_MAX; follow-ups drawn from the `stream >= 1` words)
+//   pol/C/cnt: phase-A results; tm: timestamp_mem (updated in place)
+//   shot_mode: 0 none, 1 injected (reads sq.shot_rand), 2 philox candidate with uniform u
 template <int R, class VoxAdd, class Emit>
 __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq, const FrameSc& fs,
-                                             const FrameGlobals& g, int n, int p, float diff,
-                                             int cnt, float I, float pos, float neg, float& tm,
-                                             int shot_mode, unsigned shot_word, VoxAdd vox_add,
-                                             Emit emit) {
-    const float pol = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                                             const FrameGlobals& g, int n, int p, float pol,
+                                             float C, int cnt, float I, float& tm, int shot_mode,
+                                             float u, VoxAdd vox_add, Emit emit) {
     int final_cnt = 0;
     int last = cnt;  // iterations [0,last) can produce events
-    ShotThr thr;
+    double thr64 = 0.;
+    float thr32 = 0.f, p_it = 0.f;
     int next_shot = 0x7fffffff;
-    unsigned follow = 1;
-    float p_it = 0.f;
+    unsigned follow = 2;
+    const bool up = pol > 0.f;
     if (shot_mode && g.mx > 0 && pol != 0.f) {
-        thr = shot_thresholds(cfg, g, I, pos, neg);
+        // emulator_utils.py:173-188: factor = ((rate/2)*dt/ni) * ((0.25-1)*inten01 + 1);
+        // ON fires when rand > 1 - factor*ppp, OFF when rand < factor*npp (f32 or f64, trap T5)
+        const float fac = fadd(fmul(cfg.shot_inten_m1, I), 1.0f);
+        const float pp = fmul(up ? cfg.rn_pos : cfg.rn_neg, C);
+        if (g.f64) {
+            const double q = __dmul_rn(__dmul_rn(g.a64, (double)fac), (double)pp);
+            thr64 = up ? __dsub_rn(1.0, q) : q;
+            p_it = (float)q;
+        } else {
+            const float q = fmul(fmul(g.a32, fac), pp);
+            thr32 = up ? fsub(1.0f, q) : q;
+            p_it = q;
+        }
         if (shot_mode == 1) {
             last = g.mx;
         } else {
-            p_it = pol > 0.f ? thr.p_on : thr.p_off;
-            next_shot = geometric_skip(u32_to_unit(shot_word), p_it);
-            if (next_shot < g.mx) last = g.mx;  // conservatively walk to mx (rare path)
+            next_shot = geometric_skip(u, p_it);
+            if (next_shot < g.mx) last = g.mx;  // walk to mx (rare path)
         }
-    } else if (shot_mode == 1 && g.mx > 0) {
-        last = cnt;  // pol == 0: shot events are masked out (v2e_model.py:447)
     }
     if (last > g.mx) last = g.mx;
     for (int i = 0; i < last; ++i) {
         bool m = cnt >= i + 1;
         if (shot_mode == 1 && pol != 0.f) {
-            const float r = __ldg(sq.shot_rand + ((long long)(n - 1) * sq.shot_imax + i) * cfg.P + p);
-            bool on, off;
-            if (g.f64) { on = (double)r > thr.on64; off = (double)r < thr.off64; }
-            else { on = r > thr.on32; off = r < thr.off32; }
-            const bool s = (on && pol > 0.f) || (off && pol < 0.f);
-            if (sq.dbg_shot && i < sq.dbg_shot_imax)
-                sq.dbg_shot[((long long)(n - 1) * sq.dbg_shot_imax + i) * cfg.P + p] = s;
+            const float r =
+                __ldg(sq.shot_rand + ((long long)(n - 1) * sq.shot_imax + i) * cfg.P + p);
+            bool s;
+            if (g.f64) s = up ? ((double)r > thr64) : ((double)r < thr64);
+            else s = up ? (r > thr32) : (r < thr32);
             m = m || s;
         } else if (shot_mode == 2 && i == next_shot) {
             if (sq.dbg_shot && i < sq.dbg_shot_imax)
                 sq.dbg_shot[((long long)(n - 1) * sq.dbg_shot_imax + i) * cfg.P + p] = 1;
             m = true;
             const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, (unsigned)n,
-                                           (unsigned)p, follow++);
-            const int gap = geometric_skip(u32_to_unit(w.x), p_it);
+                                           (unsigned)p, follow);
+            follow = follow < 0x7fu ? follow + 1 : follow;
+            const int gap = geometric_skip((float)(w.x >> 8) * (1.0f / 16777216.0f), p_it);
             next_shot = gap >= 0x7fffffff - i - 1 ? 0x7fffffff : i + 1 + gap;
         }
         const float ts = fadd(fs.t_bin_prev, fmul(g.ts_step, (float)(i + 1)));

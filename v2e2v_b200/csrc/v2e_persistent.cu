@@ -19,12 +19,14 @@
 
 namespace v2e {
 
-constexpr int kPThreads = 512;  // one CTA per SM
-constexpr int kPPT = 16;        // pixels per thread (4 groups of 4)
+constexpr int kPThreads = 896;  // 28 warps = 7 per SMSP, one CTA per SM, <= 72 registers per thread
+constexpr int kPPT = 8;         // pixels per thread (2 groups of 4)
 constexpr int kGroups = kPPT / 4;
 constexpr int kTileMaxPx = kPThreads * kPPT;
 constexpr int kStagesMax = 3;
 constexpr int kHeaderBytes = 4096;  // LUT, mbarriers, reduction scratch, TileCtx
+constexpr int kWarps = kPThreads / 32;
+static_assert(kTileMaxPx <= 8192, "queue entries hold a 13-bit pixel index");
 
 struct PersistParams {
     CfgDev cfg;
@@ -73,50 +75,46 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, un
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Wait until `count` CTAs have arrived.  Polls with relaxed (L2) loads — an acquire load per poll
+// would invalidate the SM's L1 every iteration — and acquires once at the end.
+__device__ __forceinline__ void wait_arrivals(const unsigned* p, unsigned count) {
+    while (ld_relaxed(p) < count) {}
+    (void)ld_acquire(p);
+}
 
-// per-CTA constants kept in shared memory for the out-of-line event path
+// per-CTA constants kept in shared memory for the event path
 struct TileCtx {
     CfgDev cfg;
     SeqDev sq;
     FrameSc fs;
     FrameGlobals g;
     int n;
-    int tile_px0;      // first pixel of the tile (global pixel index)
-    int tile_px;       // pixels in this tile
-    float* s_tmem;
-    float* s_vox;
-    unsigned long long* raw_count;
 };
-
 static_assert(sizeof(TileCtx) <= 704, "TileCtx must fit its shared-memory slot");
 
-// Out-of-line event path for one pixel (3 % of pixel-frames): iteration loop on smem state.
-template <int R>
-__device__ __noinline__ int tile_iterate(const TileCtx* c, int lp_idx, float diff, int cnt, float I,
-                                         float pos, float neg, int shot_mode, unsigned word) {
-    const int p = c->tile_px0 + lp_idx;
-    float tm = c->s_tmem[lp_idx];
-    float* vox = c->s_vox;
-    const int tile_px = c->tile_px;
-    const int fin = iterate_pixel<R>(
-        c->cfg, c->sq, c->fs, c->g, c->n, p, diff, cnt, I, pos, neg, tm, shot_mode, word,
-        [&](int b, float v) { vox[b * tile_px + lp_idx] = fadd(vox[b * tile_px + lp_idx], v); },
-        [&](float ts, float polf) {
-            const unsigned long long slot = atomicAdd(c->raw_count, 1ull);
-            if ((long long)slot < c->sq.raw_capacity) {
-                float* row = c->sq.raw_events + 5 * slot;
-                const int y = p / c->cfg.W;
-                row[0] = ts; row[1] = (float)(p - y * c->cfg.W); row[2] = (float)y;
-                row[3] = polf; row[4] = 0.f;
-            }
-        });
-    c->s_tmem[lp_idx] = tm;
-    return fin;
+// Event-queue entry (one 32-bit word per flagged pixel-frame):
+//   [12:0] pixel index inside the tile, [13] polarity is ON, [14] shot candidate, [31:15] count.
+// After processing, the slot holds the f32 bits of the memory update pol*final*C (:522).
+__device__ __forceinline__ unsigned q_pack(int lidx, bool up, bool cand, int cnt) {
+    return (unsigned)lidx | ((unsigned)up << 13) | ((unsigned)cand << 14) |
+           ((unsigned)min(cnt, 0x1ffff) << 15);
+}
+
+template <int FDT>
+__device__ __forceinline__ float ring_px(const unsigned char* s_frame, int lidx) {
+    if (FDT == V2E_DT_F32) return *(const float*)(s_frame + lidx * 4);
+    if (FDT == V2E_DT_U8) return (float)s_frame[lidx];
+    return __uint_as_float(((unsigned)*(const unsigned short*)(s_frame + lidx * 2)) << 16);
 }
 
 template <int FDT, int R>
@@ -144,14 +142,16 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     // ---- shared memory carve-up ------------------------------------------------------------
     float2* s_lut = (float2*)smem_raw;                                   // 2 KB
     unsigned long long* s_bar = (unsigned long long*)(smem_raw + 2048);  // kStagesMax mbarriers
-    int* s_red = (int*)(smem_raw + 2048 + 64);                           // 16 warps
-    int* s_bcast = s_red + 32;
-    TileCtx* s_ctx = (TileCtx*)(smem_raw + 2048 + 64 + 256);             // <= 704 B
-    double* s_dred = (double*)(smem_raw + 3072);                         // 16 warps x 4
+    int* s_red = (int*)(smem_raw + 2048 + 64);                           // one int per warp
+    float* s_stat = (float*)(smem_raw + 2048 + 64 + 128);                // mean, den, on
+    int* s_qcount = (int*)(smem_raw + 2048 + 64 + 128 + 32);
+    TileCtx* s_ctx = (TileCtx*)(smem_raw + 2304);                        // <= 704 B
+    double* s_dred = (double*)(smem_raw + 3072);                         // kWarps x 4
     unsigned char* s_ring = smem_raw + kHeaderBytes;
     const int stage_bytes = (tile_px_alloc * prm.frame_elem + 127) & ~127;
     float* s_tmem = (float*)(s_ring + (size_t)prm.stages * stage_bytes);
     float* s_vox = s_tmem + tile_px_alloc;
+    unsigned* s_q = (unsigned*)(s_vox + (size_t)nb * tile_px_alloc);     // tile_px entries
 
     const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
     const bool shot = cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF;
@@ -165,11 +165,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_ctx->cfg = cfg;
         s_ctx->sq = sq;
-        s_ctx->tile_px0 = tile_px0;
-        s_ctx->tile_px = tile_px;
-        s_ctx->s_tmem = s_tmem;
-        s_ctx->s_vox = s_vox;
-        s_ctx->raw_count = &wk.raw_count;
+        *s_qcount = 0;
     }
     __syncthreads();
     // kick off the first frames of the pack (they do not depend on any state)
@@ -245,13 +241,16 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         const int st = use_ring ? (n - 1) % prm.stages : 0;
         const unsigned char* s_frame = s_ring + (size_t)st * stage_bytes;
         if (use_ring && ngroups > 0) mbar_wait(&s_bar[st], ((n - 1) / prm.stages) & 1);
+        const float shot_c32 = (float)fs.shot_c;
 
-        // ---- phase A: low-pass, leak, diff, count; flags for the event path ---------------
+        // ---- phase A: low-pass, leak, diff, count; flagged pixels go to the event queue ------
         int lmax = 0;
-        unsigned evmask = 0, candmask = 0;
+        unsigned flags = 0;      // bit j: pixel j was queued this frame
+        int slot[kGroups];       // first queue slot of each group's entries
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
             const int gl = g * kPThreads + tid;
+            slot[g] = 0;
             if (gl < ngroups) {
                 const int p0 = tile_px0 + gl * 4;
                 float4 x4;
@@ -269,25 +268,23 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     x4 = load_frame4<FDT>(sq.frames, (long long)n * P + p0);
                 }
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
-                uint4 w_shot = make_uint4(0, 0, 0, 0);
-                if (leak) {
-                    if (philox) {
-                        const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n,
-                                                       (unsigned)(g0 + gl), 0x80);
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if (philox) {
+                    w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, (unsigned)(g0 + gl), 0);
+                    if (leak) {
                         box_muller16(w.x, z[0], z[1]);
                         box_muller16(w.y, z[2], z[3]);
                         if (sq.dbg_leak_randn)
                             *(float4*)(sq.dbg_leak_randn + (size_t)(n - 1) * P + p0) =
                                 make_float4(z[0], z[1], z[2], z[3]);
-                    } else {
-                        const float4 zz = __ldg((const float4*)(sq.leak_randn + (size_t)(n - 1) * P + p0));
-                        z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
                     }
+                } else if (leak) {
+                    const float4 zz = __ldg((const float4*)(sq.leak_randn + (size_t)(n - 1) * P + p0));
+                    z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
                 }
-                if (shot && philox)
-                    w_shot = noise_words<R>(sq.philox_seed, sq.philox_offset, n, (unsigned)(g0 + gl), 0);
-                const unsigned ws[4] = {w_shot.x, w_shot.y, w_shot.z, w_shot.w};
                 const float* xp = &x4.x;
+                unsigned ent[4];
+                unsigned gflags = 0;
                 signed char polb[4];
                 int cntb[4];
 #pragma unroll
@@ -303,21 +300,32 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     }
                     if (leak) base[j] = leak_sub(base[j], lkn[j], cfg.leak_jitter, z[e], fs.sdt, pos[j]);
                     const PixelA a = diff_count(nw, base[j], pos[j], neg[j]);
-                    const int pol = a.diff > 0.f ? 1 : (a.diff < 0.f ? -1 : 0);
                     lmax = max(lmax, a.cnt);
-                    if (a.cnt > 0) evmask |= 1u << j;
-                    if (shot && pol != 0) {
+                    bool cand = false;
+                    if (shot && a.pol != 0.f) {
                         if (philox) {
-                            const float bound = shot_any_bound(cfg, (float)fs.shot_c, I,
-                                                               pol > 0 ? pos[j] : neg[j],
-                                                               pol > 0 ? cfg.rn_pos : cfg.rn_neg);
-                            if (u32_to_unit(ws[e]) < bound) candmask |= 1u << j;
+                            const float bound = shot_any_bound(cfg, shot_c32, I, a.C,
+                                                               a.pol > 0.f ? cfg.rn_pos : cfg.rn_neg);
+                            const unsigned byte = (w.z >> (8 * e)) & 0xffu;
+                            if (__builtin_expect(shot_stage1(byte, bound), 0))
+                                cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p0 + e, byte) < bound;
                         } else {
-                            candmask |= 1u << j;  // injected draws: every pol != 0 pixel iterates
+                            cand = true;  // injected draws: every pol != 0 pixel walks its iterations
                         }
                     }
-                    polb[e] = (signed char)pol;
+                    if (a.cnt > 0 || cand) gflags |= 1u << e;
+                    ent[e] = q_pack(gl * 4 + e, a.pol > 0.f, cand, a.cnt);
+                    polb[e] = (signed char)a.pol;
                     cntb[e] = a.cnt;
+                }
+                if (gflags) {
+                    const int s0 = atomicAdd(s_qcount, __popc(gflags));
+                    slot[g] = s0;
+                    int k = s0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if ((gflags >> e) & 1u) s_q[k++] = ent[e];
+                    flags |= gflags << (4 * g);
                 }
                 if (sq.dbg_pol)
                     *(char4*)(sq.dbg_pol + (size_t)(n - 1) * P + p0) =
@@ -337,17 +345,17 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         if (tid == 0) {
             int m = 0;
 #pragma unroll
-            for (int i = 0; i < kPThreads / 32; ++i) m = max(m, s_red[i]);
+            for (int i = 0; i < kWarps; ++i) m = max(m, s_red[i]);
             if (m > 0) atomicMax(&wk.gmax[n], m);
             red_release_add(&wk.arrive[n], 1u);
-            while (ld_acquire(&wk.arrive[n]) < (unsigned)prm.tiles_per_seq) {}
-            const int mx = *(volatile int*)&wk.gmax[n];
+            wait_arrivals(&wk.arrive[n], (unsigned)prm.tiles_per_seq);
+            const int mx = (int)ld_relaxed((const unsigned*)&wk.gmax[n]);
             s_ctx->fs = fs;
             s_ctx->n = n;
             s_ctx->g = frame_globals(mx, sq.duration, sq.Tr, fs.shot_c, (sq.shot_f64_mask >> n) & 1u);
             if (tile == 0 && sq.max_iters) sq.max_iters[n] = mx;
-            // every thread has consumed the previous frame's stage (it passed the barrier
-            // above after its phase B): refill it with the frame `stages` ahead
+            // every thread is past its use of the previous frame's stage: refill it with the
+            // frame `stages` ahead
             if (use_ring && ngroups > 0 && n >= 2) {
                 const int nn = n - 1 + prm.stages;
                 if (nn < T) {
@@ -361,52 +369,67 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         }
         __syncthreads();
 
-        // ---- phase B: event path for flagged pixels (v2e_model.py:449-522) -----------------
-        const int mx = s_ctx->g.mx;
-        unsigned todo = evmask | (mx > 0 ? candmask : 0u);
-        if (todo) {
-#pragma unroll
-            for (int j = 0; j < kPPT; ++j) {
-                if ((todo >> j) & 1u) {
-                    const int g = j >> 2, e = j & 3;
-                    const int gl = g * kPThreads + tid;
-                    const int lidx = gl * 4 + e;
-                    // recompute this pixel's diff / count (cheaper than keeping 16 more registers)
-                    float x;
-                    if (use_ring) {
-                        if (FDT == V2E_DT_F32) x = *(const float*)(s_frame + lidx * 4);
-                        else if (FDT == V2E_DT_U8) x = (float)s_frame[lidx];
-                        else x = __uint_as_float(((unsigned)*(const unsigned short*)(s_frame + lidx * 2)) << 16);
-                    } else {
-                        x = load_frame1<FDT>(sq.frames, (long long)n * P + tile_px0 + lidx);
-                    }
-                    float L, I;
+        // ---- phase B: the CTA drains the event queue, one entry per thread -------------------
+        {
+            const int qn = *s_qcount;
+            const FrameGlobals g = s_ctx->g;
+            const int mode_cand = philox ? 2 : 1;
+            for (int q = tid; q < qn; q += kPThreads) {
+                const unsigned e = s_q[q];
+                const int lidx = (int)(e & 0x1fffu);
+                const bool up = (e >> 13) & 1u;
+                const bool cand = (e >> 14) & 1u;
+                const int cnt = (int)(e >> 15);
+                const int p = tile_px0 + lidx;
+                const float C = up ? __ldg(sq.pos + p) : __ldg(sq.neg + p);
+                float I = 0.f, u = 0.f;
+                int mode = 0;
+                if (cand && g.mx > 0) {
+                    mode = mode_cand;
+                    const float x = use_ring ? ring_px<FDT>(s_frame, lidx)
+                                             : load_frame1<FDT>(sq.frames, (long long)n * P + p);
+                    float L;
                     log_inten(s_lut, x, L, I);
-                    const float nw = cfg.cutoff_on ? lpv[j] : L;
-                    const PixelA a = diff_count(nw, base[j], pos[j], neg[j]);
-                    const bool cand = (candmask >> j) & 1u;
-                    int mode = 0;
-                    unsigned word = 0;
-                    if (cand && mx > 0) {
-                        mode = philox ? 2 : 1;
-                        if (philox) {
-                            const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n,
-                                                           (unsigned)(g0 + gl), 0);
-                            const unsigned ws[4] = {w.x, w.y, w.z, w.w};
-                            word = ws[e];
+                    if (philox) {
+                        const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, (unsigned)(p >> 2), 0);
+                        u = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p, (w.z >> (8 * (p & 3))) & 0xffu);
+                    }
+                }
+                float tm = s_tmem[lidx];
+                const float polf = up ? 1.f : -1.f;
+                const int fin = iterate_pixel<R>(
+                    s_ctx->cfg, s_ctx->sq, s_ctx->fs, g, n, p, polf, C, cnt, I, tm, mode, u,
+                    [&](int b, float v) { s_vox[b * tile_px + lidx] = fadd(s_vox[b * tile_px + lidx], v); },
+                    [&](float ts, float pl) {
+                        const unsigned long long sl = atomicAdd(&wk.raw_count, 1ull);
+                        if ((long long)sl < sq.raw_capacity) {
+                            float* row = sq.raw_events + 5 * sl;
+                            const int y = p / cfg.W;
+                            row[0] = ts; row[1] = (float)(p - y * cfg.W); row[2] = (float)y;
+                            row[3] = pl; row[4] = 0.f;
                         }
-                    }
-                    const int fin = tile_iterate<R>(s_ctx, lidx, a.diff, a.cnt, I, pos[j], neg[j], mode, word);
-                    if (fin > 0) {
-                        const float C = a.diff > 0.f ? pos[j] : neg[j];
-                        const float polf = a.diff > 0.f ? 1.f : -1.f;
-                        base[j] = fadd(base[j], fmul(fmul(polf, (float)fin), C));  // :522
-                        nev += fin;
-                        if (sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + tile_px0 + lidx] = fin;
-                    }
+                    });
+                s_tmem[lidx] = tm;
+                // memory update pol*final*C (:522), applied by the pixel's owner below
+                s_q[q] = __float_as_uint(fin > 0 ? fmul(fmul(polf, (float)fin), C) : 0.f);
+                nev += fin;
+                if (fin > 0 && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
+            }
+        }
+        __syncthreads();
+        if (flags) {
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g) {
+                int k = slot[g];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = g * 4 + e;
+                    if ((flags >> j) & 1u) base[j] = fadd(base[j], __uint_as_float(s_q[k++]));
                 }
             }
         }
+        __syncthreads();  // queue slots are reused by the next frame
+        if (tid == 0) *s_qcount = 0;
     }
 
     // ---- write back the dynamic state ----------------------------------------------------------
@@ -451,14 +474,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     const int fin_slot = V2E_MAX_FRAMES;  // barrier slot of the final (statistics) barrier
     if (tid == 0) {
         double a = 0., b = 0., c = 0., d = 0.;
-        for (int i = 0; i < kPThreads / 32; ++i) {
+        for (int i = 0; i < kWarps; ++i) {
             a += s_dred[i * 4]; b += s_dred[i * 4 + 1]; c += s_dred[i * 4 + 2]; d += s_dred[i * 4 + 3];
         }
         wk.partials[3 * tile] = a; wk.partials[3 * tile + 1] = b; wk.partials[3 * tile + 2] = c;
         if (d > 0.) atomicAdd(&wk.nev, (unsigned long long)d);
         __threadfence();
         red_release_add(&wk.arrive[fin_slot], 1u);
-        while (ld_acquire(&wk.arrive[fin_slot]) < (unsigned)prm.tiles_per_seq) {}
+        wait_arrivals(&wk.arrive[fin_slot], (unsigned)prm.tiles_per_seq);
         // fixed-order combine: deterministic, identical in every CTA of the sequence
         a = b = c = 0.;
         for (int i = 0; i < prm.tiles_per_seq; ++i) {
@@ -470,18 +493,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
             den = fadd(sqrtf(fsub(fdiv((float)b, (float)c), fmul(mean, mean))), 1e-8f);
             on = 1.f;
         }
-        float* s_stat = (float*)s_bcast;
         s_stat[0] = mean; s_stat[1] = den; s_stat[2] = on;
-        if (tile == 0) {
-            const unsigned long long total = *(volatile unsigned long long*)&wk.nev;
-            *sq.num_events = total;
-        }
+        if (tile == 0) *sq.num_events = __ldcg(&wk.nev);
     }
     __syncthreads();
 
     // ---- normalise and store the voxel tile (utils/event_process.py:175) ------------------------
     if (voxel_out) {
-        const float* s_stat = (const float*)s_bcast;
         const float mean = s_stat[0], den = s_stat[1];
         const bool norm = s_stat[2] != 0.f;
         for (int b = 0; b < nb; ++b) {
@@ -563,7 +581,8 @@ static PersistPlan make_plan(const CfgDev& cfg, int frame_dtype, int n_seq) {
     if (tg * 4 > kTileMaxPx) return pl;
     tiles = (total_groups + tg - 1) / tg;
     const bool tma_ok = ((size_t)cfg.P * fe) % 16 == 0;
-    const size_t fixed = kHeaderBytes + (size_t)tg * 4 * sizeof(float) * (1 + cfg.nb);
+    // header + timestamp_mem + num_bins voxel planes + event queue (one word per pixel)
+    const size_t fixed = kHeaderBytes + (size_t)tg * 4 * sizeof(float) * (2 + cfg.nb);
     int stages = 0;
     if (tma_ok) {
         const size_t sb = ((size_t)tg * 4 * fe + 127) & ~(size_t)127;

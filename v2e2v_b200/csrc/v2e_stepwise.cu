@@ -74,17 +74,15 @@ __global__ void __launch_bounds__(kThreads) k_phase_a(const __grid_constant__ St
     // one thread per 4-pixel group so the Philox stream layout matches the persistent engine
     const int G4 = (P + 3) / 4;
     for (int G = blockIdx.x * blockDim.x + threadIdx.x; G < G4; G += gridDim.x * blockDim.x) {
-        uint4 w_shot = make_uint4(0, 0, 0, 0);
+        uint4 w = make_uint4(0, 0, 0, 0);
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (philox) {
-            if (shot) w_shot = noise_words<R>(sq.philox_seed, sq.philox_offset, n, G, 0);
+            w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, G, 0);
             if (leak) {
-                const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, G, 0x80);
                 box_muller16(w.x, z[0], z[1]);
                 box_muller16(w.y, z[2], z[3]);
             }
         }
-        const unsigned ws[4] = {w_shot.x, w_shot.y, w_shot.z, w_shot.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int p = 4 * G + e;
@@ -109,12 +107,14 @@ __global__ void __launch_bounds__(kThreads) k_phase_a(const __grid_constant__ St
                 sq.base[p] = base;
             }
             const PixelA a = diff_count(nw, base, pos, neg);
-            const int pol = a.diff > 0.f ? 1 : (a.diff < 0.f ? -1 : 0);
+            const int pol = (int)a.pol;
             int cand = 0;
             if (philox && shot && pol != 0) {
-                const float bound = shot_any_bound(cfg, (float)fs.shot_c, I, pol > 0 ? pos : neg,
+                const float bound = shot_any_bound(cfg, (float)fs.shot_c, I, a.C,
                                                    pol > 0 ? cfg.rn_pos : cfg.rn_neg);
-                cand = u32_to_unit(ws[e]) < bound;
+                const unsigned byte = (w.z >> (8 * e)) & 0xffu;
+                if (shot_stage1(byte, bound))
+                    cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p, byte) < bound;
             }
             cntpol[p] = (a.cnt << 3) | (cand << 2) | (pol + 1);
             lmax = max(lmax, a.cnt);
@@ -159,24 +159,21 @@ __global__ void __launch_bounds__(kThreads) k_phase_b(const __grid_constant__ St
         int fin = 0;
         const bool inj_shot = shot && !philox && mx > 0 && pol != 0;
         if (cnt > 0 || cand || inj_shot) {
-            const float pos = sq.pos[p], neg = sq.neg[p];
-            const float C = pol > 0 ? pos : neg;
-            float I = 0.f;
-            unsigned word = 0;
+            const float C = pol > 0 ? sq.pos[p] : sq.neg[p];
+            float I = 0.f, u = 0.f;
             if (shot) {
                 float L;
                 log_inten(s_lut, load_frame1<FDT>(sq.frames, (long long)n * P + p), L, I);
                 if (philox && cand) {
                     const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, p >> 2, 0);
-                    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
-                    word = ws[p & 3];
+                    u = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p,
+                                        (w.z >> (8 * (p & 3))) & 0xffu);
                 }
             }
             float tm = sq.tmem[p];
-            const float diff = pol > 0 ? 1.f : -1.f;  // only the sign is used from here on
             const int mode = inj_shot ? 1 : (cand ? 2 : 0);
             fin = iterate_pixel<R>(
-                cfg, sq, fs, g, n, p, pol == 0 ? 0.f : diff, cnt, I, pos, neg, tm, mode, word,
+                cfg, sq, fs, g, n, p, (float)pol, pol == 0 ? 0.f : C, cnt, I, tm, mode, u,
                 [&](int b, float v) { vox[(size_t)b * P + p] = fadd(vox[(size_t)b * P + p], v); },
                 [&](float ts, float polf) {
                     const unsigned long long slot = atomicAdd(&wk.raw_count, 1ull);

@@ -100,7 +100,8 @@ class EventEmulator(nn.Module):
             normalize: bool = True,
             raw_capacity: Optional[int] = None,
             debug_maps: bool = False,
-            debug_shot_imax: int = 24):
+            debug_shot_imax: int = 24,
+            lazy_num_events: bool = False):
         super().__init__()
         if output_mode not in ("raw", "voxel_grid"):
             raise ValueError("output_mode must be 'raw' or 'voxel_grid'")
@@ -161,6 +162,7 @@ class EventEmulator(nn.Module):
         self.raw_capacity = raw_capacity
         self.debug_maps = debug_maps
         self.debug_shot_imax = debug_shot_imax
+        self.lazy_num_events = lazy_num_events
         self.last_debug = {}
         self.noise_rate_array = None
         self.timestamp_mem = None
@@ -372,6 +374,10 @@ class EventEmulator(nn.Module):
                          self.timestamp_mem, out, num_events, self._workspace)
 
         self.last_debug = dict(max_iters=mx, **dbg)
+        if self.lazy_num_events and self.output_mode != "raw":
+            # extension: keep the pipeline asynchronous; num_events is a 1-element device tensor
+            self.num_events = num_events
+            return out, num_events
         n = int(num_events.item())          # python int, like the reference (forces a sync)
         self.num_events = n
         if self.output_mode == "raw":
