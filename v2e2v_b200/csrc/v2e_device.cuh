@@ -170,16 +170,16 @@ __device__ __forceinline__ void box_muller16(unsigned w, float& z0, float& z1) {
 // run before the per-frame max is known.  One uniform u decides: u >= bound -> nothing (exact);
 // u < bound -> candidate, and the same u gives the first firing iteration by inverting the
 // geometric law (exact); later firings use fresh uniforms.
-__device__ __forceinline__ float shot_any_bound(const CfgDev& cfg, float shot_c32, float I,
-                                                float thr, float rn) {
-    const float fac = fmaf(cfg.shot_inten_m1, I, 1.0f);
-    return shot_c32 * fac * (rn * thr) * 1.0001f;  // +1e-4 relative slack over rounding
+// bound*256 for one pixel: shot_k = f32(shot_c)*256*1.0001 (+1e-4 relative slack over rounding)
+__device__ __forceinline__ float shot_frame_k(double shot_c) {
+    return (float)shot_c * 256.0f * 1.0001f;
 }
-
-// First stage: u = (byte + u2)/256 with u2 drawn only if the byte alone cannot exclude u < bound.
-__device__ __forceinline__ bool shot_stage1(unsigned byte, float bound) {
-    return (float)byte < bound * 256.0f;  // byte/256 <= u, so byte/256 >= bound -> u >= bound
+__device__ __forceinline__ float shot_thr256(const CfgDev& cfg, float shot_k, float I, float thr,
+                                             float rn) {
+    return shot_k * fmaf(cfg.shot_inten_m1, I, 1.0f) * (rn * thr);
 }
+// The uniform is u = (byte + u2)/256 with u2 drawn (shot_uniform) only if the byte alone cannot
+// exclude u < bound:  byte >= 256*bound  =>  u >= bound.  Candidate iff 256*u < 256*bound.
 
 template <int R>
 static __device__ __noinline__ float shot_uniform(unsigned long long seed,
@@ -189,12 +189,21 @@ static __device__ __noinline__ float shot_uniform(unsigned long long seed,
     return ((float)byte + (float)w.x * (1.0f / 4294967296.0f)) * (1.0f / 256.0f);
 }
 
-// Geometric skip: index of the first success of iid Bernoulli(p) trials, from one uniform.
+// Geometric skip: index of the first success of iid Bernoulli(p) trials, from one uniform:
+// floor(log1p(-u)/log1p(-p)).  Both arguments are tiny in practice (u < bound ~ 5e-4), where the
+// series -log1p(-x) = x + x^2/2 + x^3/3 + x^4/4 (relative error < x^4) is exact to f32 rounding.
 static __device__ __noinline__ int geometric_skip(float u, float p) {
     if (!(p > 0.f)) return 0x7fffffff;
     if (p >= 1.f) return 0;
-    const double g = floor(log1p(-(double)u) / log1p(-(double)p));
-    return g > 2.0e9 ? 0x7fffffff : (int)g;
+    float g;
+    if (u < 0.03f && p < 0.03f) {
+        const float lu = u * fmaf(u, fmaf(u, fmaf(u, 0.25f, 0.33333334f), 0.5f), 1.0f);
+        const float lq = p * fmaf(p, fmaf(p, fmaf(p, 0.25f, 0.33333334f), 0.5f), 1.0f);
+        g = floorf(__fdividef(lu, lq));
+    } else {
+        g = (float)floor(log1p(-(double)u) / log1p(-(double)p));
+    }
+    return g > 2.0e9f ? 0x7fffffff : (int)g;
 }
 
 // ---- sensing-diversity pattern ------------------------------------------------------------------

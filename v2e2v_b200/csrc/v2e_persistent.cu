@@ -13,7 +13,7 @@
 // one arrival counter per frame per sequence (release/acquire at gpu scope), and one more
 // barrier for the normalisation statistics (utils/event_process.py:166-175).  CTAs of different
 // sequences never wait for each other.  Cooperative launch guarantees co-residency.
-#include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "v2e_engine.cuh"
 
@@ -36,6 +36,7 @@ struct PersistParams {
     int stages;        // frame ring depth (0: frames are read straight from global memory)
     int frame_elem;    // bytes per frame element
     SeqWork* work;
+    long long* timeline;  // development aid (V2E_TIMELINE=1): [cta][frame][8] clock64 stamps
     SeqDev seq[V2E_MAX_SEQ_PER_LAUNCH];
     FrameSc fr[V2E_MAX_SEQ_PER_LAUNCH][V2E_MAX_FRAMES];
 };
@@ -117,9 +118,12 @@ __device__ __forceinline__ float ring_px(const unsigned char* s_frame, int lidx)
     return __uint_as_float(((unsigned)*(const unsigned short*)(s_frame + lidx * 2)) << 16);
 }
 
-template <int FDT, int R>
+// NOISE: 0 = no noise, 1 = PHILOX leak + shot (the V2E2VNet wiring), 2 = generic: every feature
+// flag is read at run time, debug outputs and injected noise are honoured (tests, odd configs).
+template <int FDT, int R, int NOISE, bool CUTOFF>
 __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_constant__ PersistParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool GENERIC = NOISE == 2;
     const CfgDev& cfg = prm.cfg;
     const int seq = blockIdx.x / prm.tiles_per_seq;
     const int tile = blockIdx.x - seq * prm.tiles_per_seq;
@@ -129,6 +133,12 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     const int nb = cfg.nb;
     const int T = sq.T;
     const int tid = threadIdx.x;
+
+    const bool leak = GENERIC ? (cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF) : (NOISE == 1);
+    const bool shot = GENERIC ? (cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF) : (NOISE == 1);
+    const bool philox = GENERIC ? (cfg.noise_mode == V2E_NOISE_PHILOX) : (NOISE == 1);
+    const bool cutoff = GENERIC ? (cfg.cutoff_on != 0) : CUTOFF;
+    long long* tl = GENERIC ? prm.timeline : nullptr;  // thread-0 time stamps (development aid)
 
     // ---- tile geometry -------------------------------------------------------------------
     const int total_groups = P >> 2;  // P % 4 == 0 is a precondition of this engine
@@ -153,9 +163,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     float* s_vox = s_tmem + tile_px_alloc;
     unsigned* s_q = (unsigned*)(s_vox + (size_t)nb * tile_px_alloc);     // tile_px entries
 
-    const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
-    const bool shot = cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF;
-    const bool philox = cfg.noise_mode == V2E_NOISE_PHILOX;
     const bool use_ring = prm.stages > 0;
     const unsigned frame_bytes = (unsigned)(tile_px * prm.frame_elem);
 
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                 t4 = make_float4(t0, t0, t0, t0);
             } else {
                 b4 = *(const float4*)(sq.base + p0);
-                if (cfg.cutoff_on) l4 = *(const float4*)(sq.lp + p0);
+                if (cutoff) l4 = *(const float4*)(sq.lp + p0);
                 t4 = *(const float4*)(sq.tmem + p0);
                 // rollover (v2e_model.py:329-330)
                 float* tp = &t4.x;
@@ -221,6 +228,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
             *(float4*)(s_tmem + gl * 4) = t4;
             for (int b = 0; b < nb; ++b)
                 *(float4*)(s_vox + b * tile_px + gl * 4) = make_float4(0, 0, 0, 0);
+            const int y = p0 / cfg.W, x = p0 - y * cfg.W;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                int xe = x + e, ye = y;
+                if (xe >= cfg.W) { xe -= cfg.W; ye += 1; }   // a group may straddle a row end
+                if (xe >= cfg.W) { xe -= cfg.W; ye += 1; }
+                if (((xe | ye) & 1) == 0) small_mask |= 1u << (g * 4 + e);
+            }
         }
         const float* bp = &b4.x; const float* lp_ = &l4.x; const float* pp = &ps4.x;
         const float* np_ = &ng4.x; const float* rp = &nr4.x;
@@ -229,19 +244,24 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
             const int j = g * 4 + e;
             base[j] = bp[e]; lpv[j] = lp_[e]; pos[j] = pp[e]; neg[j] = np_[e];
             lkn[j] = fmul(cfg.leak_rate, rp[e]);
-            if (valid && is_small_px(p0 + e, cfg.W)) small_mask |= 1u << j;
         }
     }
     __syncthreads();
 
     long long nev = 0;
+    const float jit = cfg.leak_jitter;
+    const bool rn_same = cfg.rn_pos == cfg.rn_neg;
     // ---- time-step over the frames of the pack ---------------------------------------------
     for (int n = 1; n < T; ++n) {
         const FrameSc& fs = prm.fr[seq][n];
         const int st = use_ring ? (n - 1) % prm.stages : 0;
         const unsigned char* s_frame = s_ring + (size_t)st * stage_bytes;
+        if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 0] = clock64();
         if (use_ring && ngroups > 0) mbar_wait(&s_bar[st], ((n - 1) / prm.stages) & 1);
-        const float shot_c32 = (float)fs.shot_c;
+        if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 1] = clock64();
+        const float s_small = fs.s_small, s_large = fs.s_large, sdt = fs.sdt;
+        // stage-1 shot threshold factor: byte < 256*bound, bound = shot_c*fac*(rn*C)*1.0001
+        const float shot_k = shot_frame_k(fs.shot_c);
 
         // ---- phase A: low-pass, leak, diff, count; flagged pixels go to the event queue ------
         int lmax = 0;
@@ -268,13 +288,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     x4 = load_frame4<FDT>(sq.frames, (long long)n * P + p0);
                 }
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
-                uint4 w = make_uint4(0, 0, 0, 0);
+                unsigned shot_bytes = 0;
                 if (philox) {
-                    w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, (unsigned)(g0 + gl), 0);
+                    const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, (unsigned)(g0 + gl), 0);
+                    shot_bytes = w.z;
                     if (leak) {
                         box_muller16(w.x, z[0], z[1]);
                         box_muller16(w.y, z[2], z[3]);
-                        if (sq.dbg_leak_randn)
+                        if (GENERIC && sq.dbg_leak_randn)
                             *(float4*)(sq.dbg_leak_randn + (size_t)(n - 1) * P + p0) =
                                 make_float4(z[0], z[1], z[2], z[3]);
                     }
@@ -293,30 +314,31 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     float L, I;
                     log_inten(s_lut, xp[e], L, I);
                     float nw = L;
-                    if (cfg.cutoff_on) {
-                        const float s = (small_mask >> j) & 1u ? fs.s_small : fs.s_large;
+                    if (cutoff) {
+                        const float s = (small_mask >> j) & 1u ? s_small : s_large;
                         lpv[j] = lowpass(lpv[j], L, I, s);
                         nw = lpv[j];
                     }
-                    if (leak) base[j] = leak_sub(base[j], lkn[j], cfg.leak_jitter, z[e], fs.sdt, pos[j]);
+                    if (leak) base[j] = leak_sub(base[j], lkn[j], jit, z[e], sdt, pos[j]);
                     const PixelA a = diff_count(nw, base[j], pos[j], neg[j]);
-                    lmax = max(lmax, a.cnt);
                     bool cand = false;
                     if (shot && a.pol != 0.f) {
                         if (philox) {
-                            const float bound = shot_any_bound(cfg, shot_c32, I, a.C,
-                                                               a.pol > 0.f ? cfg.rn_pos : cfg.rn_neg);
-                            const unsigned byte = (w.z >> (8 * e)) & 0xffu;
-                            if (__builtin_expect(shot_stage1(byte, bound), 0))
-                                cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p0 + e, byte) < bound;
+                            const float rn = rn_same ? cfg.rn_pos : (a.pol > 0.f ? cfg.rn_pos : cfg.rn_neg);
+                            const float thr256 = shot_thr256(cfg, shot_k, I, a.C, rn);
+                            const unsigned byte = (shot_bytes >> (8 * e)) & 0xffu;
+                            if (__builtin_expect((float)byte < thr256, 0))
+                                cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p0 + e, byte) * 256.0f < thr256;
                         } else {
                             cand = true;  // injected draws: every pol != 0 pixel walks its iterations
                         }
                     }
-                    if (a.cnt > 0 || cand) gflags |= 1u << e;
+                    if (__builtin_expect(a.cnt > 0 || cand, 0)) {
+                        gflags |= 1u << e;
+                        lmax = max(lmax, a.cnt);
+                    }
                     ent[e] = q_pack(gl * 4 + e, a.pol > 0.f, cand, a.cnt);
-                    polb[e] = (signed char)a.pol;
-                    cntb[e] = a.cnt;
+                    if (GENERIC) { polb[e] = (signed char)a.pol; cntb[e] = a.cnt; }
                 }
                 if (gflags) {
                     const int s0 = atomicAdd(s_qcount, __popc(gflags));
@@ -327,29 +349,35 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                         if ((gflags >> e) & 1u) s_q[k++] = ent[e];
                     flags |= gflags << (4 * g);
                 }
-                if (sq.dbg_pol)
-                    *(char4*)(sq.dbg_pol + (size_t)(n - 1) * P + p0) =
-                        make_char4(polb[0], polb[1], polb[2], polb[3]);
-                if (sq.dbg_cnt)
-                    *(int4*)(sq.dbg_cnt + (size_t)(n - 1) * P + p0) =
-                        make_int4(cntb[0], cntb[1], cntb[2], cntb[3]);
-                if (sq.dbg_final)
-                    *(int4*)(sq.dbg_final + (size_t)(n - 1) * P + p0) = make_int4(0, 0, 0, 0);
+                if (GENERIC) {
+                    if (sq.dbg_pol)
+                        *(char4*)(sq.dbg_pol + (size_t)(n - 1) * P + p0) =
+                            make_char4(polb[0], polb[1], polb[2], polb[3]);
+                    if (sq.dbg_cnt)
+                        *(int4*)(sq.dbg_cnt + (size_t)(n - 1) * P + p0) =
+                            make_int4(cntb[0], cntb[1], cntb[2], cntb[3]);
+                    if (sq.dbg_final)
+                        *(int4*)(sq.dbg_final + (size_t)(n - 1) * P + p0) = make_int4(0, 0, 0, 0);
+                }
             }
         }
+        if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 2] = clock64();
 
         // ---- per-sequence max over all tiles (v2e_model.py:405-406) -----------------------
         lmax = __reduce_max_sync(0xffffffffu, lmax);
         if ((tid & 31) == 0) s_red[tid >> 5] = lmax;
         __syncthreads();
         if (tid == 0) {
+            if (tl) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 3] = clock64();
             int m = 0;
 #pragma unroll
             for (int i = 0; i < kWarps; ++i) m = max(m, s_red[i]);
             if (m > 0) atomicMax(&wk.gmax[n], m);
             red_release_add(&wk.arrive[n], 1u);
+            if (tl) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 4] = clock64();
             wait_arrivals(&wk.arrive[n], (unsigned)prm.tiles_per_seq);
             const int mx = (int)ld_relaxed((const unsigned*)&wk.gmax[n]);
+            if (tl) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 5] = clock64();
             s_ctx->fs = fs;
             s_ctx->n = n;
             s_ctx->g = frame_globals(mx, sq.duration, sq.Tr, fs.shot_c, (sq.shot_f64_mask >> n) & 1u);
@@ -368,6 +396,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
             }
         }
         __syncthreads();
+        if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 6] = clock64();
 
         // ---- phase B: the CTA drains the event queue, one entry per thread -------------------
         {
@@ -413,9 +442,10 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                 // memory update pol*final*C (:522), applied by the pixel's owner below
                 s_q[q] = __float_as_uint(fin > 0 ? fmul(fmul(polf, (float)fin), C) : 0.f);
                 nev += fin;
-                if (fin > 0 && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
+                if (GENERIC && fin > 0 && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
             }
         }
+        if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 7] = clock64();
         __syncthreads();
         if (flags) {
 #pragma unroll
@@ -440,7 +470,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         if (gl < ngroups) {
             const int p0 = tile_px0 + gl * 4;
             *(float4*)(sq.base + p0) = make_float4(base[g * 4], base[g * 4 + 1], base[g * 4 + 2], base[g * 4 + 3]);
-            if (cfg.cutoff_on)
+            if (cutoff)
                 *(float4*)(sq.lp + p0) = make_float4(lpv[g * 4], lpv[g * 4 + 1], lpv[g * 4 + 2], lpv[g * 4 + 3]);
             *(float4*)(sq.tmem + p0) = *(const float4*)(s_tmem + gl * 4);
         }
@@ -472,29 +502,41 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     }
     __syncthreads();
     const int fin_slot = V2E_MAX_FRAMES;  // barrier slot of the final (statistics) barrier
-    if (tid == 0) {
-        double a = 0., b = 0., c = 0., d = 0.;
-        for (int i = 0; i < kWarps; ++i) {
-            a += s_dred[i * 4]; b += s_dred[i * 4 + 1]; c += s_dred[i * 4 + 2]; d += s_dred[i * 4 + 3];
+    if (tid < 32) {
+        // warp 0: publish this tile's partial sums, wait for the other tiles, combine
+        if (tid == 0) {
+            double a = 0., b = 0., c = 0., d = 0.;
+            for (int i = 0; i < kWarps; ++i) {
+                a += s_dred[i * 4]; b += s_dred[i * 4 + 1]; c += s_dred[i * 4 + 2]; d += s_dred[i * 4 + 3];
+            }
+            wk.partials[3 * tile] = a; wk.partials[3 * tile + 1] = b; wk.partials[3 * tile + 2] = c;
+            if (d > 0.) atomicAdd(&wk.nev, (unsigned long long)d);
+            __threadfence();
+            red_release_add(&wk.arrive[fin_slot], 1u);
+            wait_arrivals(&wk.arrive[fin_slot], (unsigned)prm.tiles_per_seq);
         }
-        wk.partials[3 * tile] = a; wk.partials[3 * tile + 1] = b; wk.partials[3 * tile + 2] = c;
-        if (d > 0.) atomicAdd(&wk.nev, (unsigned long long)d);
-        __threadfence();
-        red_release_add(&wk.arrive[fin_slot], 1u);
-        wait_arrivals(&wk.arrive[fin_slot], (unsigned)prm.tiles_per_seq);
-        // fixed-order combine: deterministic, identical in every CTA of the sequence
-        a = b = c = 0.;
-        for (int i = 0; i < prm.tiles_per_seq; ++i) {
+        __syncwarp();
+        // fixed assignment tile -> lane and a fixed shuffle tree: deterministic, and identical in
+        // every CTA of the sequence
+        double a = 0., b = 0., c = 0.;
+        for (int i = tid; i < prm.tiles_per_seq; i += 32) {
             a += __ldcg(&wk.partials[3 * i]); b += __ldcg(&wk.partials[3 * i + 1]); c += __ldcg(&wk.partials[3 * i + 2]);
         }
-        float mean = 0.f, den = 1.f, on = 0.f;
-        if (c > 0. && cfg.output_mode == V2E_OUT_VOXEL) {
-            mean = fdiv((float)a, (float)c);
-            den = fadd(sqrtf(fsub(fdiv((float)b, (float)c), fmul(mean, mean))), 1e-8f);
-            on = 1.f;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
         }
-        s_stat[0] = mean; s_stat[1] = den; s_stat[2] = on;
-        if (tile == 0) *sq.num_events = __ldcg(&wk.nev);
+        if (tid == 0) {
+            float mean = 0.f, den = 1.f, on = 0.f;
+            if (c > 0. && cfg.output_mode == V2E_OUT_VOXEL) {
+                mean = fdiv((float)a, (float)c);
+                den = fadd(sqrtf(fsub(fdiv((float)b, (float)c), fmul(mean, mean))), 1e-8f);
+                on = 1.f;
+            }
+            s_stat[0] = mean; s_stat[1] = den; s_stat[2] = on;
+            if (tile == 0) *sq.num_events = __ldcg(&wk.nev);
+        }
     }
     __syncthreads();
 
@@ -607,9 +649,28 @@ int persistent_fits(const CfgDev& cfg, int frame_dtype, int n_seq) {
     return make_plan(cfg, frame_dtype, n_seq).ok;
 }
 
-template <int FDT, int R>
-static int run_persistent_t(const CfgDev& cfg, const v2e_pack* packs, int n_seq, void* workspace,
-                            cudaStream_t st) {
+template <int FDT, int R, int NOISE, bool CUTOFF>
+static int launch_persistent(const PersistParams& prm, const PersistPlan& pl, cudaStream_t st) {
+    static bool attr_set = false;  // one process drives one device (see DESIGN.md, multi-GPU)
+    auto kern = k_persistent<FDT, R, NOISE, CUTOFF>;
+    int rc = V2E_OK;
+    if (!attr_set) {
+        rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          g_smem_optin));
+        if (rc != V2E_OK) return rc;
+        attr_set = true;
+    }
+    void* args[] = {(void*)&prm};
+    const dim3 grid((unsigned)(pl.tiles_per_seq * prm.n_seq));
+    rc = cuda_ok(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(kPThreads), args,
+                                             pl.smem, st));
+    count_launch();
+    return rc;
+}
+
+template <int FDT>
+static int run_persistent_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, int n_seq,
+                            void* workspace, cudaStream_t st) {
     const PersistPlan pl = make_plan(cfg, FDT, n_seq);
     if (!pl.ok) return V2E_ERR_UNSUPPORTED;
     static thread_local PersistParams prm;  // 16 KB: keep it off the stack
@@ -620,40 +681,51 @@ static int run_persistent_t(const CfgDev& cfg, const v2e_pack* packs, int n_seq,
     prm.stages = pl.stages;
     prm.frame_elem = frame_elem_bytes(FDT);
     prm.work = (SeqWork*)workspace;
+    static const bool want_timeline = getenv("V2E_TIMELINE") != nullptr;
+    // the stepwise engine's accumulator area of the workspace is unused here: borrow it
+    prm.timeline = want_timeline ? (long long*)((char*)workspace + step_layout(cfg, n_seq).vox_off)
+                                 : nullptr;
+    bool dbg = want_timeline;
     for (int s = 0; s < n_seq; ++s) {
         fill_seq(prm.seq[s], packs[s]);
         for (int n = 1; n < packs[s].sc.num_frames; ++n) {
             const v2e_frame_scalars& f = packs[s].sc.fr[n];
             prm.fr[s][n] = FrameSc{f.t_bin_prev, f.s_large, f.s_small, f.sdt, f.shot_c};
         }
+        const v2e_pack& p = packs[s];
+        dbg = dbg || p.dbg_pol || p.dbg_cnt || p.dbg_final || p.dbg_leak_randn || p.dbg_shot;
     }
-    static bool attr_set = false;  // one process drives one device (see DESIGN.md, multi-GPU)
-    auto kern = k_persistent<FDT, R>;
-    int rc = V2E_OK;
-    if (!attr_set) {
-        rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          g_smem_optin));
-        if (rc != V2E_OK) return rc;
-        attr_set = true;
+    const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
+    const bool shot = cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF;
+    const bool philox = cfg.noise_mode == V2E_NOISE_PHILOX;
+    // fast variants: no debug outputs, voxel output, and either no noise or PHILOX leak+shot
+    int noise = 2;
+    if (!dbg && cfg.output_mode != V2E_OUT_RAW) {
+        if (!leak && !shot) noise = 0;
+        else if (philox && leak && shot) noise = 1;
     }
-    void* args[] = {(void*)&prm};
-    const dim3 grid((unsigned)(pl.tiles_per_seq * n_seq));
-    rc = cuda_ok(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(kPThreads), args, pl.smem, st));
-    count_launch();
-    return rc;
+    const bool r7 = rounds == 7;
+    if (noise == 0)
+        return cfg.cutoff_on ? launch_persistent<FDT, 10, 0, true>(prm, pl, st)
+                             : launch_persistent<FDT, 10, 0, false>(prm, pl, st);
+    if (noise == 1) {
+        if (cfg.cutoff_on)
+            return r7 ? launch_persistent<FDT, 7, 1, true>(prm, pl, st)
+                      : launch_persistent<FDT, 10, 1, true>(prm, pl, st);
+        return r7 ? launch_persistent<FDT, 7, 1, false>(prm, pl, st)
+                  : launch_persistent<FDT, 10, 1, false>(prm, pl, st);
+    }
+    return r7 ? launch_persistent<FDT, 7, 2, false>(prm, pl, st)
+              : launch_persistent<FDT, 10, 2, false>(prm, pl, st);
 }
 
 int run_persistent(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs,
                    int n_seq, void* workspace, cudaStream_t st) {
-#define V2E_DISPATCH(FDT)                                                               \
-    return rounds == 7 ? run_persistent_t<FDT, 7>(cfg, packs, n_seq, workspace, st)     \
-                       : run_persistent_t<FDT, 10>(cfg, packs, n_seq, workspace, st)
     switch (frame_dtype) {
-        case V2E_DT_U8: V2E_DISPATCH(V2E_DT_U8);
-        case V2E_DT_BF16: V2E_DISPATCH(V2E_DT_BF16);
-        default: V2E_DISPATCH(V2E_DT_F32);
+        case V2E_DT_U8: return run_persistent_t<V2E_DT_U8>(cfg, rounds, packs, n_seq, workspace, st);
+        case V2E_DT_BF16: return run_persistent_t<V2E_DT_BF16>(cfg, rounds, packs, n_seq, workspace, st);
+        default: return run_persistent_t<V2E_DT_F32>(cfg, rounds, packs, n_seq, workspace, st);
     }
-#undef V2E_DISPATCH
 }
 
 }  // namespace v2e

@@ -110,11 +110,11 @@ __global__ void __launch_bounds__(kThreads) k_phase_a(const __grid_constant__ St
             const int pol = (int)a.pol;
             int cand = 0;
             if (philox && shot && pol != 0) {
-                const float bound = shot_any_bound(cfg, (float)fs.shot_c, I, a.C,
-                                                   pol > 0 ? cfg.rn_pos : cfg.rn_neg);
+                const float thr256 = shot_thr256(cfg, shot_frame_k(fs.shot_c), I, a.C,
+                                                 pol > 0 ? cfg.rn_pos : cfg.rn_neg);
                 const unsigned byte = (w.z >> (8 * e)) & 0xffu;
-                if (shot_stage1(byte, bound))
-                    cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p, byte) < bound;
+                if ((float)byte < thr256)
+                    cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p, byte) * 256.0f < thr256;
             }
             cntpol[p] = (a.cnt << 3) | (cand << 2) | (pol + 1);
             lmax = max(lmax, a.cnt);
