@@ -37,8 +37,7 @@ struct SeqDev {
     int* dbg_final;
     float* dbg_leak_randn;
     unsigned char* dbg_shot;
-    unsigned long long philox_seed;
-    unsigned long long philox_offset;
+    unsigned long long philox_ctr;  // splitmix64(seed) + pack offset: the (z,w) counter words
     // pack scalars
     float Tr, duration, bins_m1;
     int first_pack;
@@ -124,43 +123,54 @@ __device__ __forceinline__ float4 load_frame4(const void* __restrict__ f, long l
 }
 
 // ---- Philox4x32 (Salmon et al., SC'11), R rounds ------------------------------------------------
+// The key is a library constant (all per-emulator entropy sits in the 128-bit counter), so the
+// key schedule folds into immediates: a round is 2 IMAD.WIDE + 2 three-input XORs.
 template <int R>
-__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr) {
+    unsigned k0 = 0xA4093822u, k1 = 0x299F31D0u;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u;
-        key.y += 0xBB67AE85u;
+        const unsigned long long p0 = (unsigned long long)ctr.x * 0xD2511F53ull;
+        const unsigned long long p1 = (unsigned long long)ctr.z * 0xCD9E8D57ull;
+        ctr = make_uint4((unsigned)(p1 >> 32) ^ ctr.y ^ k0, (unsigned)p1,
+                         (unsigned)(p0 >> 32) ^ ctr.w ^ k1, (unsigned)p0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
     }
     return ctr;
 }
 
-// Noise words: a pure function of (seed, pack offset, frame n, index, stream), hence identical in
-// both engines.
+// Noise words: a pure function of (counter base, frame n, index, stream), hence identical in both
+// engines.  ctr64 = splitmix64(seed) + pack counter (host side, fill_seq).
 //   stream 0, index = 4-pixel group G: .x/.y -> leak normals of pixels (0,1)/(2,3) of the group,
 //                                      .z    -> one byte per pixel: first stage of the shot test
 //   stream 1.., index = pixel p:       .x    -> second-stage / follow-up shot uniforms (rare)
 template <int R>
-__device__ __forceinline__ uint4 noise_words(unsigned long long seed, unsigned long long offset,
-                                             unsigned n, unsigned index, unsigned stream) {
-    const uint4 ctr =
-        make_uint4(index, n | (stream << 8), (unsigned)offset, (unsigned)(offset >> 32));
-    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
-    return philox4x32<R>(ctr, key);
+__device__ __forceinline__ uint4 noise_words(unsigned long long ctr64, unsigned n, unsigned index,
+                                             unsigned stream) {
+    return philox4x32<R>(
+        make_uint4(index, n | (stream << 8), (unsigned)ctr64, (unsigned)(ctr64 >> 32)));
 }
 
-// Two standard normals from one 32-bit word: u1 = (lo16+1)/65536 in (0,1], u2 = hi16/65536.
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Two standard normals from one 32-bit word (Box-Muller): u1 = (lo16+1)/65536 in (0,1],
+// u2 = hi16/65536.  r = sqrt(-2 ln u1) = sqrt(-2 ln2 * (log2(lo16+1) - 16)).
 __device__ __forceinline__ void box_muller16(unsigned w, float& z0, float& z1) {
-    const float u1 = (float)((w & 0xffffu) + 1u) * (1.0f / 65536.0f);
-    const float u2 = (float)(w >> 16) * (1.0f / 65536.0f);
-    // sqrt(-2 ln u1) = sqrt(-2 ln2 * log2(u1))
-    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));
-    float s, c;
-    __sincosf(6.283185307179586f * u2, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    const float a = (float)((w & 0xffffu) + 1u);
+    const float r = sqrt_approx(fmaf(lg2_approx(a), -1.3862943611198906f, 22.18070977791825f));
+    const float t = (float)(w >> 16) * (6.283185307179586f / 65536.0f);
+    z0 = r * __cosf(t);
+    z1 = r * __sinf(t);
 }
 
 // ---- shot noise in PHILOX mode: distribution-equivalent skip-ahead ------------------------------
@@ -182,10 +192,9 @@ __device__ __forceinline__ float shot_thr256(const CfgDev& cfg, float shot_k, fl
 // exclude u < bound:  byte >= 256*bound  =>  u >= bound.  Candidate iff 256*u < 256*bound.
 
 template <int R>
-static __device__ __noinline__ float shot_uniform(unsigned long long seed,
-                                                  unsigned long long offset, int n, int p,
+static __device__ __noinline__ float shot_uniform(unsigned long long ctr64, int n, int p,
                                                   unsigned byte) {
-    const uint4 w = noise_words<R>(seed, offset, (unsigned)n, (unsigned)p, 1);
+    const uint4 w = noise_words<R>(ctr64, (unsigned)n, (unsigned)p, 1);
     return ((float)byte + (float)w.x * (1.0f / 4294967296.0f)) * (1.0f / 256.0f);
 }
 
@@ -255,21 +264,14 @@ struct FrameGlobals {
     int mx;
     float ts_step;
     int gate;
-    int f64;
-    double a64;
-    float a32;
 };
 
-__device__ __forceinline__ FrameGlobals frame_globals(int mx, float duration, float Tr,
-                                                      double shot_c, bool f64) {
+__device__ __forceinline__ FrameGlobals frame_globals(int mx, float duration, float Tr) {
     FrameGlobals g;
     g.mx = mx;
     const int ni = mx > 0 ? mx : 1;
     g.ts_step = fmul(__frcp_rn((float)ni), duration);  // reciprocal()*duration (trap T6)
     g.gate = Tr > g.ts_step;
-    g.f64 = f64;
-    g.a64 = shot_c / (double)ni;
-    g.a32 = fdiv((float)shot_c, (float)ni);
     return g;
 }
 
@@ -289,18 +291,24 @@ __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq
     float thr32 = 0.f, p_it = 0.f;
     int next_shot = 0x7fffffff;
     unsigned follow = 2;
+    bool f64 = false;
     const bool up = pol > 0.f;
     if (shot_mode && g.mx > 0 && pol != 0.f) {
         // emulator_utils.py:173-188: factor = ((rate/2)*dt/ni) * ((0.25-1)*inten01 + 1);
         // ON fires when rand > 1 - factor*ppp, OFF when rand < factor*npp (f32 or f64, trap T5)
         const float fac = fadd(fmul(cfg.shot_inten_m1, I), 1.0f);
         const float pp = fmul(up ? cfg.rn_pos : cfg.rn_neg, C);
-        if (g.f64) {
-            const double q = __dmul_rn(__dmul_rn(g.a64, (double)fac), (double)pp);
+        const int ni = g.mx;  // > 0 here, so num_iters == mx
+        f64 = (sq.shot_f64_mask >> n) & 1u;
+        if (f64) {
+            // (rate/2)*dt / num_iters in f64 (emulator_utils.py:174, trap T5)
+            const double a64 = fs.shot_c / (double)ni;
+            const double q = __dmul_rn(__dmul_rn(a64, (double)fac), (double)pp);
             thr64 = up ? __dsub_rn(1.0, q) : q;
             p_it = (float)q;
         } else {
-            const float q = fmul(fmul(g.a32, fac), pp);
+            const float a32 = fdiv((float)fs.shot_c, (float)ni);
+            const float q = fmul(fmul(a32, fac), pp);
             thr32 = up ? fsub(1.0f, q) : q;
             p_it = q;
         }
@@ -318,14 +326,14 @@ __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq
             const float r =
                 __ldg(sq.shot_rand + ((long long)(n - 1) * sq.shot_imax + i) * cfg.P + p);
             bool s;
-            if (g.f64) s = up ? ((double)r > thr64) : ((double)r < thr64);
+            if (f64) s = up ? ((double)r > thr64) : ((double)r < thr64);
             else s = up ? (r > thr32) : (r < thr32);
             m = m || s;
         } else if (shot_mode == 2 && i == next_shot) {
             if (sq.dbg_shot && i < sq.dbg_shot_imax)
                 sq.dbg_shot[((long long)(n - 1) * sq.dbg_shot_imax + i) * cfg.P + p] = 1;
             m = true;
-            const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, (unsigned)n,
+            const uint4 w = noise_words<R>(sq.philox_ctr, (unsigned)n,
                                            (unsigned)p, follow);
             follow = follow < 0x7fu ? follow + 1 : follow;
             const int gap = geometric_skip((float)(w.x >> 8) * (1.0f / 16777216.0f), p_it);

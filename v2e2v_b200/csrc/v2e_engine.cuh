@@ -12,8 +12,9 @@ constexpr int kMaxPartials = 2048;
 
 // Per-sequence work area inside the caller's workspace.  Zero on entry, zero on exit.
 struct SeqWork {
-    int gmax[V2E_MAX_FRAMES];             // per-frame max event count (atomicMax)
-    unsigned arrive[V2E_MAX_FRAMES + 4];  // persistent engine: per-frame barrier arrivals
+    // per-frame barrier word: low half = CTAs arrived (persistent engine), high half = max
+    // event count of the frame (atomicMax); slot V2E_MAX_FRAMES is the statistics barrier
+    unsigned long long bar[V2E_MAX_FRAMES + 4];
     unsigned long long raw_count;         // raw mode: rows appended
     unsigned long long nev;               // persistent engine: event counter
     unsigned exit_count;                  // persistent engine: CTAs that left (last one cleans)
@@ -42,6 +43,13 @@ inline StepLayout step_layout(const CfgDev& cfg, int n_seq) {
     return l;
 }
 
+inline unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
 inline void fill_seq(SeqDev& d, const v2e_pack& p) {
     d.frames = p.frames;
     d.base = p.base_log_frame;
@@ -64,8 +72,7 @@ inline void fill_seq(SeqDev& d, const v2e_pack& p) {
     d.dbg_final = p.dbg_final;
     d.dbg_leak_randn = p.dbg_leak_randn;
     d.dbg_shot = p.dbg_shot;
-    d.philox_seed = p.philox_seed;
-    d.philox_offset = p.philox_offset;
+    d.philox_ctr = splitmix64(p.philox_seed) + p.philox_offset;
     d.Tr = p.sc.Tr;
     d.duration = p.sc.duration;
     d.bins_m1 = p.sc.bins_m1;

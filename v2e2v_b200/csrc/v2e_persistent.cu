@@ -24,7 +24,8 @@ constexpr int kPPT = 8;         // pixels per thread (2 groups of 4)
 constexpr int kGroups = kPPT / 4;
 constexpr int kTileMaxPx = kPThreads * kPPT;
 constexpr int kStagesMax = 3;
-constexpr int kHeaderBytes = 4096;  // LUT, mbarriers, reduction scratch, TileCtx
+constexpr int kHeaderBytes = 4608;  // LUT, mbarriers, reduction scratch, TileCtx, candidate table
+constexpr int kCandCap = 64;        // shot candidates per CTA-frame kept with their uniform
 constexpr int kWarps = kPThreads / 32;
 static_assert(kTileMaxPx <= 8192, "queue entries hold a 13-bit pixel index");
 
@@ -86,8 +87,24 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Wait until `count` CTAs have arrived.  Polls with relaxed (L2) loads — an acquire load per poll
-// would invalidate the SM's L1 every iteration — and acquires once at the end.
+// Per-frame barrier word: low 32 bits = arrivals, high 32 bits = running max of the event counts.
+// A CTA publishes its max (relaxed atomicMax on the high half) and then arrives with release
+// semantics on the low half; both halves live in one 8-byte word served by one L2 slice, so a
+// single relaxed 64-bit load that observes all arrivals also observes every max.  Polling uses
+// relaxed (L2) loads: an acquire load per poll would invalidate the SM's L1 every iteration.
+__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int frame_barrier(unsigned long long* bar, int my_max, unsigned count) {
+    if (my_max > 0) atomicMax((int*)bar + 1, my_max);
+    red_release_add((unsigned*)bar, 1u);
+    unsigned long long v;
+    do { v = ld_relaxed64(bar); } while ((unsigned)v < count);
+    return (int)(v >> 32);
+}
+// Barrier that also orders ordinary data written before it (used once, for the statistics).
 __device__ __forceinline__ void wait_arrivals(const unsigned* p, unsigned count) {
     while (ld_relaxed(p) < count) {}
     (void)ld_acquire(p);
@@ -97,15 +114,18 @@ __device__ __forceinline__ void wait_arrivals(const unsigned* p, unsigned count)
 struct TileCtx {
     CfgDev cfg;
     SeqDev sq;
-    FrameSc fs;
-    FrameGlobals g;
-    int n;
 };
 static_assert(sizeof(TileCtx) <= 704, "TileCtx must fit its shared-memory slot");
 
+struct CandEntry {  // shot candidate found in phase A: pixel (tile-local) and its uniform
+    int lidx;
+    float u;
+};
+
 // Event-queue entry (one 32-bit word per flagged pixel-frame):
 //   [12:0] pixel index inside the tile, [13] polarity is ON, [14] shot candidate, [31:15] count.
-// After processing, the slot holds the f32 bits of the memory update pol*final*C (:522).
+// After processing, the slot holds pol*final_evts_frame as a signed int; the pixel's owner turns it
+// into the memory update (pol*final)*C (:522) with its own copy of the thresholds.
 __device__ __forceinline__ unsigned q_pack(int lidx, bool up, bool cand, int cnt) {
     return (unsigned)lidx | ((unsigned)up << 13) | ((unsigned)cand << 14) |
            ((unsigned)min(cnt, 0x1ffff) << 15);
@@ -152,11 +172,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     // ---- shared memory carve-up ------------------------------------------------------------
     float2* s_lut = (float2*)smem_raw;                                   // 2 KB
     unsigned long long* s_bar = (unsigned long long*)(smem_raw + 2048);  // kStagesMax mbarriers
-    int* s_red = (int*)(smem_raw + 2048 + 64);                           // one int per warp
-    float* s_stat = (float*)(smem_raw + 2048 + 64 + 128);                // mean, den, on
-    int* s_qcount = (int*)(smem_raw + 2048 + 64 + 128 + 32);
+    int* s_red = (int*)(smem_raw + 2112);                                // one int per warp
+    float* s_stat = (float*)(smem_raw + 2240);                           // mean, den, on
+    int* s_qcount = (int*)(smem_raw + 2272);
+    int* s_ncand = (int*)(smem_raw + 2276);
+    int* s_mx = (int*)(smem_raw + 2280);
     TileCtx* s_ctx = (TileCtx*)(smem_raw + 2304);                        // <= 704 B
     double* s_dred = (double*)(smem_raw + 3072);                         // kWarps x 4
+    CandEntry* s_cand = (CandEntry*)(smem_raw + 4096);                   // kCandCap x 8 B
     unsigned char* s_ring = smem_raw + kHeaderBytes;
     const int stage_bytes = (tile_px_alloc * prm.frame_elem + 127) & ~127;
     float* s_tmem = (float*)(s_ring + (size_t)prm.stages * stage_bytes);
@@ -173,6 +196,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         s_ctx->cfg = cfg;
         s_ctx->sq = sq;
         *s_qcount = 0;
+        *s_ncand = 0;
     }
     __syncthreads();
     // kick off the first frames of the pack (they do not depend on any state)
@@ -251,6 +275,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     long long nev = 0;
     const float jit = cfg.leak_jitter;
     const bool rn_same = cfg.rn_pos == cfg.rn_neg;
+    const float shot_m1 = cfg.shot_inten_m1;
     // ---- time-step over the frames of the pack ---------------------------------------------
     for (int n = 1; n < T; ++n) {
         const FrameSc& fs = prm.fr[seq][n];
@@ -260,7 +285,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         if (use_ring && ngroups > 0) mbar_wait(&s_bar[st], ((n - 1) / prm.stages) & 1);
         if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 1] = clock64();
         const float s_small = fs.s_small, s_large = fs.s_large, sdt = fs.sdt;
-        // stage-1 shot threshold factor: byte < 256*bound, bound = shot_c*fac*(rn*C)*1.0001
         const float shot_k = shot_frame_k(fs.shot_c);
 
         // ---- phase A: low-pass, leak, diff, count; flagged pixels go to the event queue ------
@@ -290,7 +314,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
                 unsigned shot_bytes = 0;
                 if (philox) {
-                    const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, (unsigned)(g0 + gl), 0);
+                    const uint4 w = noise_words<R>(sq.philox_ctr, n, (unsigned)(g0 + gl), 0);
                     shot_bytes = w.z;
                     if (leak) {
                         box_muller16(w.x, z[0], z[1]);
@@ -320,25 +344,53 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                         nw = lpv[j];
                     }
                     if (leak) base[j] = leak_sub(base[j], lkn[j], jit, z[e], sdt, pos[j]);
-                    const PixelA a = diff_count(nw, base[j], pos[j], neg[j]);
-                    bool cand = false;
-                    if (shot && a.pol != 0.f) {
+                    // diff / polarity / threshold (v2e_model.py:375,394-404), see diff_count()
+                    const float diff = fsub(nw, base[j]);
+                    const float ad = fabsf(diff);
+                    const bool live = ad > 1e-6f;
+                    const bool up = diff > 0.f;
+                    const float C = live ? (up ? pos[j] : neg[j]) : 0.f;
+                    const bool cross = live && ad >= fadd(C, 1e-9f);
+                    bool maybe = cross;
+                    float thr256 = 0.f;
+                    unsigned byte = 0;
+                    if (shot) {
                         if (philox) {
-                            const float rn = rn_same ? cfg.rn_pos : (a.pol > 0.f ? cfg.rn_pos : cfg.rn_neg);
-                            const float thr256 = shot_thr256(cfg, shot_k, I, a.C, rn);
-                            const unsigned byte = (shot_bytes >> (8 * e)) & 0xffu;
-                            if (__builtin_expect((float)byte < thr256, 0))
-                                cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p0 + e, byte) * 256.0f < thr256;
+                            const float rn = rn_same ? cfg.rn_pos : (up ? cfg.rn_pos : cfg.rn_neg);
+                            thr256 = (shot_k * fmaf(shot_m1, I, 1.0f)) * (rn * C);   // 0 if !live
+                            byte = (shot_bytes >> (8 * e)) & 0xffu;
+                            maybe = maybe || (float)byte < thr256;
                         } else {
-                            cand = true;  // injected draws: every pol != 0 pixel walks its iterations
+                            maybe = maybe || live;  // injected draws: every pol != 0 pixel iterates
                         }
                     }
-                    if (__builtin_expect(a.cnt > 0 || cand, 0)) {
-                        gflags |= 1u << e;
-                        lmax = max(lmax, a.cnt);
+                    ent[e] = 0;
+                    if (GENERIC) { polb[e] = live ? (up ? 1 : -1) : 0; cntb[e] = 0; }
+                    if (__builtin_expect(maybe, 0)) {
+                        // rare path (~4 % of pixel-frames): exact count, shot second stage, queue
+                        const int cnt = cross ? count_div(ad, fadd(C, 1e-9f)) : 0;
+                        bool cand = false;
+                        if (shot && live) {
+                            if (philox) {
+                                if ((float)byte < thr256) {
+                                    const float u = shot_uniform<R>(sq.philox_ctr, n, p0 + e, byte);
+                                    cand = u * 256.0f < thr256;
+                                    if (cand) {
+                                        const int k = atomicAdd(s_ncand, 1);
+                                        if (k < kCandCap) s_cand[k] = CandEntry{gl * 4 + e, u};
+                                    }
+                                }
+                            } else {
+                                cand = true;
+                            }
+                        }
+                        if (cnt > 0 || cand) {
+                            gflags |= 1u << e;
+                            lmax = max(lmax, cnt);
+                            ent[e] = q_pack(gl * 4 + e, up, cand, cnt);
+                        }
+                        if (GENERIC) cntb[e] = cnt;
                     }
-                    ent[e] = q_pack(gl * 4 + e, a.pol > 0.f, cand, a.cnt);
-                    if (GENERIC) { polb[e] = (signed char)a.pol; cntb[e] = a.cnt; }
                 }
                 if (gflags) {
                     const int s0 = atomicAdd(s_qcount, __popc(gflags));
@@ -367,23 +419,19 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         lmax = __reduce_max_sync(0xffffffffu, lmax);
         if ((tid & 31) == 0) s_red[tid >> 5] = lmax;
         __syncthreads();
-        if (tid == 0) {
-            if (tl) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 3] = clock64();
-            int m = 0;
-#pragma unroll
-            for (int i = 0; i < kWarps; ++i) m = max(m, s_red[i]);
-            if (m > 0) atomicMax(&wk.gmax[n], m);
-            red_release_add(&wk.arrive[n], 1u);
-            if (tl) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 4] = clock64();
-            wait_arrivals(&wk.arrive[n], (unsigned)prm.tiles_per_seq);
-            const int mx = (int)ld_relaxed((const unsigned*)&wk.gmax[n]);
-            if (tl) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 5] = clock64();
-            s_ctx->fs = fs;
-            s_ctx->n = n;
-            s_ctx->g = frame_globals(mx, sq.duration, sq.Tr, fs.shot_c, (sq.shot_f64_mask >> n) & 1u);
-            if (tile == 0 && sq.max_iters) sq.max_iters[n] = mx;
+        if (tid < 32) {
+            if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 3] = clock64();
+            int m = tid < kWarps ? s_red[tid] : 0;
+            m = __reduce_max_sync(0xffffffffu, m);
+            if (tid == 0) {
+                const int mx = frame_barrier(&wk.bar[n], m, (unsigned)prm.tiles_per_seq);
+                if (tl) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 5] = clock64();
+                *s_mx = mx;
+                if (tile == 0 && sq.max_iters) sq.max_iters[n] = mx;
+            }
+        } else if (tid == 32) {
             // every thread is past its use of the previous frame's stage: refill it with the
-            // frame `stages` ahead
+            // frame `stages` ahead (off the barrier's critical path)
             if (use_ring && ngroups > 0 && n >= 2) {
                 const int nn = n - 1 + prm.stages;
                 if (nn < T) {
@@ -401,65 +449,76 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         // ---- phase B: the CTA drains the event queue, one entry per thread -------------------
         {
             const int qn = *s_qcount;
-            const FrameGlobals g = s_ctx->g;
-            const int mode_cand = philox ? 2 : 1;
-            for (int q = tid; q < qn; q += kPThreads) {
-                const unsigned e = s_q[q];
-                const int lidx = (int)(e & 0x1fffu);
-                const bool up = (e >> 13) & 1u;
-                const bool cand = (e >> 14) & 1u;
-                const int cnt = (int)(e >> 15);
-                const int p = tile_px0 + lidx;
-                const float C = up ? __ldg(sq.pos + p) : __ldg(sq.neg + p);
-                float I = 0.f, u = 0.f;
-                int mode = 0;
-                if (cand && g.mx > 0) {
-                    mode = mode_cand;
-                    const float x = use_ring ? ring_px<FDT>(s_frame, lidx)
-                                             : load_frame1<FDT>(sq.frames, (long long)n * P + p);
-                    float L;
-                    log_inten(s_lut, x, L, I);
-                    if (philox) {
-                        const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, (unsigned)(p >> 2), 0);
-                        u = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p, (w.z >> (8 * (p & 3))) & 0xffu);
-                    }
-                }
-                float tm = s_tmem[lidx];
-                const float polf = up ? 1.f : -1.f;
-                const int fin = iterate_pixel<R>(
-                    s_ctx->cfg, s_ctx->sq, s_ctx->fs, g, n, p, polf, C, cnt, I, tm, mode, u,
-                    [&](int b, float v) { s_vox[b * tile_px + lidx] = fadd(s_vox[b * tile_px + lidx], v); },
-                    [&](float ts, float pl) {
-                        const unsigned long long sl = atomicAdd(&wk.raw_count, 1ull);
-                        if ((long long)sl < sq.raw_capacity) {
-                            float* row = sq.raw_events + 5 * sl;
-                            const int y = p / cfg.W;
-                            row[0] = ts; row[1] = (float)(p - y * cfg.W); row[2] = (float)y;
-                            row[3] = pl; row[4] = 0.f;
+            if (tid < qn) {
+                const FrameGlobals g = frame_globals(*s_mx, sq.duration, sq.Tr);
+                const int ncand = min(*s_ncand, kCandCap);
+                for (int q = tid; q < qn; q += kPThreads) {
+                    const unsigned e = s_q[q];
+                    const int lidx = (int)(e & 0x1fffu);
+                    const bool up = (e >> 13) & 1u;
+                    const bool cand = (e >> 14) & 1u;
+                    const int cnt = (int)(e >> 15);
+                    const int p = tile_px0 + lidx;
+                    float I = 0.f, u = 0.f, C = 0.f;
+                    int mode = 0;
+                    if (cand && g.mx > 0) {   // rare: shot candidate (or injected shot draws)
+                        mode = philox ? 2 : 1;
+                        C = up ? __ldg(sq.pos + p) : __ldg(sq.neg + p);
+                        const float x = use_ring ? ring_px<FDT>(s_frame, lidx)
+                                                 : load_frame1<FDT>(sq.frames, (long long)n * P + p);
+                        float L;
+                        log_inten(s_lut, x, L, I);
+                        if (philox) {
+                            bool found = false;
+                            for (int k = 0; k < ncand; ++k)
+                                if (s_cand[k].lidx == lidx) { u = s_cand[k].u; found = true; }
+                            if (!found) {   // candidate table overflowed: redraw (same value)
+                                const uint4 w = noise_words<R>(sq.philox_ctr, n, (unsigned)(p >> 2), 0);
+                                u = shot_uniform<R>(sq.philox_ctr, n, p, (w.z >> (8 * (p & 3))) & 0xffu);
+                            }
                         }
-                    });
-                s_tmem[lidx] = tm;
-                // memory update pol*final*C (:522), applied by the pixel's owner below
-                s_q[q] = __float_as_uint(fin > 0 ? fmul(fmul(polf, (float)fin), C) : 0.f);
-                nev += fin;
-                if (GENERIC && fin > 0 && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
+                    }
+                    float tm = s_tmem[lidx];
+                    const float polf = up ? 1.f : -1.f;
+                    const int fin = iterate_pixel<R>(
+                        s_ctx->cfg, s_ctx->sq, fs, g, n, p, polf, C, cnt, I, tm, mode, u,
+                        [&](int b, float v) { s_vox[b * tile_px + lidx] = fadd(s_vox[b * tile_px + lidx], v); },
+                        [&](float ts, float pl) {
+                            const unsigned long long sl = atomicAdd(&wk.raw_count, 1ull);
+                            if ((long long)sl < sq.raw_capacity) {
+                                float* row = sq.raw_events + 5 * sl;
+                                const int y = p / cfg.W;
+                                row[0] = ts; row[1] = (float)(p - y * cfg.W); row[2] = (float)y;
+                                row[3] = pl; row[4] = 0.f;
+                            }
+                        });
+                    s_tmem[lidx] = tm;
+                    s_q[q] = (unsigned)(up ? fin : -fin);   // pol*final, applied by the owner below
+                    nev += fin;
+                    if (GENERIC && fin > 0 && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
+                }
             }
         }
         if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 7] = clock64();
         __syncthreads();
         if (flags) {
+            // memory update base += (pol*final)*C (v2e_model.py:522)
 #pragma unroll
             for (int g = 0; g < kGroups; ++g) {
                 int k = slot[g];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = g * 4 + e;
-                    if ((flags >> j) & 1u) base[j] = fadd(base[j], __uint_as_float(s_q[k++]));
+                    if ((flags >> j) & 1u) {
+                        const int pf = (int)s_q[k++];
+                        if (pf != 0)
+                            base[j] = fadd(base[j], fmul((float)pf, pf > 0 ? pos[j] : neg[j]));
+                    }
                 }
             }
         }
         __syncthreads();  // queue slots are reused by the next frame
-        if (tid == 0) *s_qcount = 0;
+        if (tid == 0) { *s_qcount = 0; *s_ncand = 0; }
     }
 
     // ---- write back the dynamic state ----------------------------------------------------------
@@ -512,8 +571,8 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
             wk.partials[3 * tile] = a; wk.partials[3 * tile + 1] = b; wk.partials[3 * tile + 2] = c;
             if (d > 0.) atomicAdd(&wk.nev, (unsigned long long)d);
             __threadfence();
-            red_release_add(&wk.arrive[fin_slot], 1u);
-            wait_arrivals(&wk.arrive[fin_slot], (unsigned)prm.tiles_per_seq);
+            red_release_add((unsigned*)&wk.bar[fin_slot], 1u);
+            wait_arrivals((const unsigned*)&wk.bar[fin_slot], (unsigned)prm.tiles_per_seq);
         }
         __syncwarp();
         // fixed assignment tile -> lane and a fixed shuffle tree: deterministic, and identical in
@@ -571,8 +630,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         __threadfence();
         const unsigned prev = atomicAdd(&wk.exit_count, 1u);
         if (prev == (unsigned)prm.tiles_per_seq - 1) {
-            for (int i = 0; i < V2E_MAX_FRAMES; ++i) wk.gmax[i] = 0;
-            for (int i = 0; i < V2E_MAX_FRAMES + 4; ++i) wk.arrive[i] = 0;
+            for (int i = 0; i < V2E_MAX_FRAMES + 4; ++i) wk.bar[i] = 0ull;
             wk.nev = 0ull;
             wk.raw_count = 0ull;
             __threadfence();

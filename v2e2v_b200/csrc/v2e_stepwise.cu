@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kThreads) k_phase_a(const __grid_constant__ St
         uint4 w = make_uint4(0, 0, 0, 0);
         float z[4] = {0.f, 0.f, 0.f, 0.f};
         if (philox) {
-            w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, G, 0);
+            w = noise_words<R>(sq.philox_ctr, n, G, 0);
             if (leak) {
                 box_muller16(w.x, z[0], z[1]);
                 box_muller16(w.y, z[2], z[3]);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) k_phase_a(const __grid_constant__ St
                                                  pol > 0 ? cfg.rn_pos : cfg.rn_neg);
                 const unsigned byte = (w.z >> (8 * e)) & 0xffu;
                 if ((float)byte < thr256)
-                    cand = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p, byte) * 256.0f < thr256;
+                    cand = shot_uniform<R>(sq.philox_ctr, n, p, byte) * 256.0f < thr256;
             }
             cntpol[p] = (a.cnt << 3) | (cand << 2) | (pol + 1);
             lmax = max(lmax, a.cnt);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads) k_phase_a(const __grid_constant__ St
     if (threadIdx.x == 0) {
         int m = 0;
         for (int i = 0; i < kThreads / 32; ++i) m = max(m, s_max[i]);
-        if (m > 0) atomicMax(&prm.work[blockIdx.y].gmax[n], m);
+        if (m > 0) atomicMax((int*)&prm.work[blockIdx.y].bar[n] + 1, m);
     }
 }
 
@@ -146,9 +146,8 @@ __global__ void __launch_bounds__(kThreads) k_phase_b(const __grid_constant__ St
     const bool shot = cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF;
     const bool philox = cfg.noise_mode == V2E_NOISE_PHILOX;
     StepWork& wk = prm.work[blockIdx.y];
-    const int mx = wk.gmax[n];
-    const FrameGlobals g =
-        frame_globals(mx, sq.duration, sq.Tr, fs.shot_c, (sq.shot_f64_mask >> n) & 1u);
+    const int mx = ((const int*)&wk.bar[n])[1];
+    const FrameGlobals g = frame_globals(mx, sq.duration, sq.Tr);
     if (blockIdx.x == 0 && threadIdx.x == 0 && sq.max_iters) sq.max_iters[n] = mx;
     const int* cntpol = prm.cntpol + (size_t)blockIdx.y * P;
     float* vox = prm.vox_acc + (size_t)blockIdx.y * cfg.nb * P;
@@ -165,8 +164,8 @@ __global__ void __launch_bounds__(kThreads) k_phase_b(const __grid_constant__ St
                 float L;
                 log_inten(s_lut, load_frame1<FDT>(sq.frames, (long long)n * P + p), L, I);
                 if (philox && cand) {
-                    const uint4 w = noise_words<R>(sq.philox_seed, sq.philox_offset, n, p >> 2, 0);
-                    u = shot_uniform<R>(sq.philox_seed, sq.philox_offset, n, p,
+                    const uint4 w = noise_words<R>(sq.philox_ctr, n, p >> 2, 0);
+                    u = shot_uniform<R>(sq.philox_ctr, n, p,
                                         (w.z >> (8 * (p & 3))) & 0xffu);
                 }
             }
@@ -277,7 +276,7 @@ __global__ void k_end_pack(const __grid_constant__ StepParams prm) {
     StepWork& wk = prm.work[s];
     const SeqDev& sq = prm.seq[s];
     if (threadIdx.x == 0 && prm.cfg.output_mode == V2E_OUT_RAW) wk.raw_count = 0ull;
-    for (int i = threadIdx.x; i < V2E_MAX_FRAMES; i += blockDim.x) wk.gmax[i] = 0;
+    for (int i = threadIdx.x; i < V2E_MAX_FRAMES + 4; i += blockDim.x) wk.bar[i] = 0ull;
     (void)sq;
 }
 
