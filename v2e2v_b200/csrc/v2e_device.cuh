@@ -45,9 +45,10 @@ struct SeqDev {
     int T;
 };
 
-struct FrameSc {  // per-frame scalars, index n
+struct FrameSc {  // per-frame scalars, index n (32 bytes)
     float t_bin_prev, s_large, s_small, sdt;
     double shot_c;
+    float kp, kn;  // first-stage shot factors 256*1.0001*f32(shot_c)*f32(1/nominal) (ON, OFF)
 };
 
 struct CfgDev {
@@ -180,13 +181,10 @@ __device__ __forceinline__ void box_muller16(unsigned w, float& z0, float& z1) {
 // run before the per-frame max is known.  One uniform u decides: u >= bound -> nothing (exact);
 // u < bound -> candidate, and the same u gives the first firing iteration by inverting the
 // geometric law (exact); later firings use fresh uniforms.
-// bound*256 for one pixel: shot_k = f32(shot_c)*256*1.0001 (+1e-4 relative slack over rounding)
-__device__ __forceinline__ float shot_frame_k(double shot_c) {
-    return (float)shot_c * 256.0f * 1.0001f;
-}
-__device__ __forceinline__ float shot_thr256(const CfgDev& cfg, float shot_k, float I, float thr,
-                                             float rn) {
-    return shot_k * fmaf(cfg.shot_inten_m1, I, 1.0f) * (rn * thr);
+// 256*bound for one pixel = (k_side * fac) * C with k_side = 256*1.0001*f32(shot_c)*rn_side (host,
+// make_frame_sc; the 1e-4 relative slack covers rounding) and fac = (0.25-1)*inten01 + 1.
+__device__ __forceinline__ float shot_thr256(float k_side, float shot_m1, float I, float C) {
+    return (k_side * fmaf(shot_m1, I, 1.0f)) * C;
 }
 // The uniform is u = (byte + u2)/256 with u2 drawn (shot_uniform) only if the byte alone cannot
 // exclude u < bound:  byte >= 256*bound  =>  u >= bound.  Candidate iff 256*u < 256*bound.
@@ -320,7 +318,10 @@ __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq
         }
     }
     if (last > g.mx) last = g.mx;
-    for (int i = 0; i < last; ++i) {
+    // PHILOX candidates only visit the iterations that can fire: [0,cnt) and the shot indices
+    int i = (shot_mode == 2 && cnt == 0) ? next_shot : 0;
+    for (; i < last;) {
+        const int cur = i;
         bool m = cnt >= i + 1;
         if (shot_mode == 1 && pol != 0.f) {
             const float r =
@@ -339,7 +340,9 @@ __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq
             const int gap = geometric_skip((float)(w.x >> 8) * (1.0f / 16777216.0f), p_it);
             next_shot = gap >= 0x7fffffff - i - 1 ? 0x7fffffff : i + 1 + gap;
         }
-        const float ts = fadd(fs.t_bin_prev, fmul(g.ts_step, (float)(i + 1)));
+        i = cur + 1;
+        if (shot_mode == 2 && i >= cnt && i < next_shot) i = next_shot;
+        const float ts = fadd(fs.t_bin_prev, fmul(g.ts_step, (float)(cur + 1)));
         if (g.gate) {  // v2e_model.py:469-472
             const float since = fsub(m ? ts : 0.f, tm);
             m = since > sq.Tr;

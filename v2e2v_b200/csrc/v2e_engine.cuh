@@ -81,6 +81,19 @@ inline void fill_seq(SeqDev& d, const v2e_pack& p) {
     d.T = p.sc.num_frames;
 }
 
+inline FrameSc make_frame_sc(const CfgDev& cfg, const v2e_frame_scalars& f) {
+    FrameSc s;
+    s.t_bin_prev = f.t_bin_prev;
+    s.s_large = f.s_large;
+    s.s_small = f.s_small;
+    s.sdt = f.sdt;
+    s.shot_c = f.shot_c;
+    const float k = (float)f.shot_c * 256.0f * 1.0001f;
+    s.kp = k * cfg.rn_pos;
+    s.kn = k * cfg.rn_neg;
+    return s;
+}
+
 // launch accounting + CUDA error capture (v2e_api.cu)
 void count_launch(int n = 1);
 int cuda_ok(cudaError_t e);

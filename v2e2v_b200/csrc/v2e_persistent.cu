@@ -23,8 +23,7 @@ constexpr int kPThreads = 896;  // 28 warps = 7 per SMSP, one CTA per SM, <= 72 
 constexpr int kPPT = 8;         // pixels per thread (2 groups of 4)
 constexpr int kGroups = kPPT / 4;
 constexpr int kTileMaxPx = kPThreads * kPPT;
-constexpr int kStagesMax = 3;
-constexpr int kHeaderBytes = 4608;  // LUT, mbarriers, reduction scratch, TileCtx, candidate table
+constexpr int kHeaderBytes = 6144;  // LUT, mbarrier, reduction scratch, TileCtx, candidates, frame scalars
 constexpr int kCandCap = 64;        // shot candidates per CTA-frame kept with their uniform
 constexpr int kWarps = kPThreads / 32;
 static_assert(kTileMaxPx <= 8192, "queue entries hold a 13-bit pixel index");
@@ -117,9 +116,9 @@ struct TileCtx {
 };
 static_assert(sizeof(TileCtx) <= 704, "TileCtx must fit its shared-memory slot");
 
-struct CandEntry {  // shot candidate found in phase A: pixel (tile-local) and its uniform
+struct CandEntry {  // shot candidate found in phase A: pixel (tile-local), its uniform, I and C
     int lidx;
-    float u;
+    float u, I, C;
 };
 
 // Event-queue entry (one 32-bit word per flagged pixel-frame):
@@ -136,6 +135,80 @@ __device__ __forceinline__ float ring_px(const unsigned char* s_frame, int lidx)
     if (FDT == V2E_DT_F32) return *(const float*)(s_frame + lidx * 4);
     if (FDT == V2E_DT_U8) return (float)s_frame[lidx];
     return __uint_as_float(((unsigned)*(const unsigned short*)(s_frame + lidx * 2)) << 16);
+}
+
+// shared-memory loads through a 32-bit shared-window address (saves the generic->shared address
+// arithmetic the compiler otherwise redoes at every use)
+__device__ __forceinline__ float2 lds_f2(unsigned addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u2(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+// Frame value -> (L, I) with the LUT addressed through its shared-window address.
+__device__ __forceinline__ void log_inten_s(unsigned lut_addr, float x, float& L, float& I) {
+    const int v = __float2int_rn(x);
+    float2 e;
+    if (__builtin_expect((float)v == x && (unsigned)v < 256u, 1)) e = lds_f2(lut_addr + 8u * (unsigned)v);
+    else e = log_inten_slow(x);
+    L = e.x;
+    I = e.y;
+}
+
+
+// Rare per-pixel path of phase A (~4 % of pixel-frames), out of line to keep the streaming loop
+// small: exact event count on a threshold crossing, second stage of the PHILOX shot test, and the
+// queue entry.  Returns the packed entry (0 = nothing to do) and raises lmax.
+struct RareCtx {
+    unsigned long long philox_ctr;
+    int* s_ncand;
+    CandEntry* s_cand;
+};
+template <int R>
+static __device__ __noinline__ unsigned rare_px(const RareCtx* rc, int n, int p, int lidx, float ad,
+                                                float C, float I, float thr256, unsigned flags_in,
+                                                int* lmax) {
+    // flags_in: bit0 cross, bit1 live, bit2 up, bit3 shot on, bit4 philox, bits 8..15 shot byte
+    const bool cross = flags_in & 1u, live = flags_in & 2u, up = flags_in & 4u;
+    const bool shot = flags_in & 8u, philox = flags_in & 16u;
+    const unsigned byte = (flags_in >> 8) & 0xffu;
+    const int cnt = cross ? count_div(ad, fadd(C, 1e-9f)) : 0;
+    bool cand = false;
+    if (shot && live) {
+        if (philox) {
+            if ((float)byte < thr256) {
+                const float u = shot_uniform<R>(rc->philox_ctr, n, p, byte);
+                cand = u * 256.0f < thr256;
+                if (cand) {
+                    const int k = atomicAdd(rc->s_ncand, 1);
+                    if (k < kCandCap) rc->s_cand[k] = CandEntry{lidx, u, I, C};
+                }
+            }
+        } else {
+            cand = true;  // injected draws: every pol != 0 pixel walks its iterations
+        }
+    }
+    if (cnt > 0 || cand) {
+        *lmax = max(*lmax, cnt);
+        return q_pack(lidx, up, cand, cnt);
+    }
+    return 0u;
 }
 
 // NOISE: 0 = no noise, 1 = PHILOX leak + shot (the V2E2VNet wiring), 2 = generic: every feature
@@ -171,7 +244,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
 
     // ---- shared memory carve-up ------------------------------------------------------------
     float2* s_lut = (float2*)smem_raw;                                   // 2 KB
-    unsigned long long* s_bar = (unsigned long long*)(smem_raw + 2048);  // kStagesMax mbarriers
+    unsigned long long* s_bar = (unsigned long long*)(smem_raw + 2048);  // frame mbarrier
     int* s_red = (int*)(smem_raw + 2112);                                // one int per warp
     float* s_stat = (float*)(smem_raw + 2240);                           // mean, den, on
     int* s_qcount = (int*)(smem_raw + 2272);
@@ -179,19 +252,23 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     int* s_mx = (int*)(smem_raw + 2280);
     TileCtx* s_ctx = (TileCtx*)(smem_raw + 2304);                        // <= 704 B
     double* s_dred = (double*)(smem_raw + 3072);                         // kWarps x 4
-    CandEntry* s_cand = (CandEntry*)(smem_raw + 4096);                   // kCandCap x 8 B
+    CandEntry* s_cand = (CandEntry*)(smem_raw + 4096);                   // kCandCap x 16 B
+    FrameSc* s_fr = (FrameSc*)(smem_raw + 5120);                         // V2E_MAX_FRAMES x 32 B
     unsigned char* s_ring = smem_raw + kHeaderBytes;
     const int stage_bytes = (tile_px_alloc * prm.frame_elem + 127) & ~127;
     float* s_tmem = (float*)(s_ring + (size_t)prm.stages * stage_bytes);
-    float* s_vox = s_tmem + tile_px_alloc;
+    float* s_lkn = s_tmem + tile_px_alloc;                               // leak_rate * noise_rate
+    float* s_vox = s_lkn + tile_px_alloc;
     unsigned* s_q = (unsigned*)(s_vox + (size_t)nb * tile_px_alloc);     // tile_px entries
+    const unsigned a_lut = smem_u32(s_lut), a_ring = smem_u32(s_ring), a_lkn = smem_u32(s_lkn);
 
     const bool use_ring = prm.stages > 0;
     const unsigned frame_bytes = (unsigned)(tile_px * prm.frame_elem);
 
     load_lut(s_lut, cfg.lut);
+    for (int i = tid; i < T; i += kPThreads) s_fr[i] = prm.fr[seq][i];
     if (tid == 0) {
-        for (int s = 0; s < kStagesMax; ++s) mbar_init(&s_bar[s], 1);
+        mbar_init(&s_bar[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_ctx->cfg = cfg;
         s_ctx->sq = sq;
@@ -199,19 +276,19 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         *s_ncand = 0;
     }
     __syncthreads();
-    // kick off the first frames of the pack (they do not depend on any state)
-    if (use_ring && tid == 0 && ngroups > 0) {
-        for (int n = 1; n < T && n <= prm.stages; ++n) {
-            const int st = (n - 1) % prm.stages;
-            mbar_expect_tx(&s_bar[st], frame_bytes);
-            tma_load_1d(s_ring + (size_t)st * stage_bytes,
-                        (const unsigned char*)sq.frames + ((size_t)n * P + tile_px0) * prm.frame_elem,
-                        frame_bytes, &s_bar[st]);
-        }
+    // The frame tile of step n+1 is fetched by one TMA bulk copy while step n waits for the other
+    // tiles (it does not depend on any state); the whole pack is first pulled into L2.
+    if (use_ring && tid == 32 && ngroups > 0) {
+        const unsigned char* src = (const unsigned char*)sq.frames + (size_t)tile_px0 * prm.frame_elem;
+        for (int n = 2; n < T; ++n)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)n * P * prm.frame_elem),
+                         "r"(frame_bytes) : "memory");
+        mbar_expect_tx(&s_bar[0], frame_bytes);
+        tma_load_1d(s_ring, src + (size_t)P * prm.frame_elem, frame_bytes, &s_bar[0]);
     }
 
     // ---- load per-pixel state into registers / shared memory --------------------------------
-    float base[kPPT], lpv[kPPT], pos[kPPT], neg[kPPT], lkn[kPPT];
+    float base[kPPT], lpv[kPPT], pos[kPPT], neg[kPPT];
     unsigned small_mask = 0;  // bit j: pixel j of this thread is a "small" (ps, qs) pixel
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
@@ -250,6 +327,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                 }
             }
             *(float4*)(s_tmem + gl * 4) = t4;
+            *(float4*)(s_lkn + gl * 4) =
+                make_float4(fmul(cfg.leak_rate, nr4.x), fmul(cfg.leak_rate, nr4.y),
+                            fmul(cfg.leak_rate, nr4.z), fmul(cfg.leak_rate, nr4.w));
             for (int b = 0; b < nb; ++b)
                 *(float4*)(s_vox + b * tile_px + gl * 4) = make_float4(0, 0, 0, 0);
             const int y = p0 / cfg.W, x = p0 - y * cfg.W;
@@ -262,30 +342,25 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
             }
         }
         const float* bp = &b4.x; const float* lp_ = &l4.x; const float* pp = &ps4.x;
-        const float* np_ = &ng4.x; const float* rp = &nr4.x;
+        const float* np_ = &ng4.x;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int j = g * 4 + e;
             base[j] = bp[e]; lpv[j] = lp_[e]; pos[j] = pp[e]; neg[j] = np_[e];
-            lkn[j] = fmul(cfg.leak_rate, rp[e]);
         }
     }
     __syncthreads();
 
     long long nev = 0;
+    RareCtx rctx{sq.philox_ctr, s_ncand, s_cand};
     const float jit = cfg.leak_jitter;
-    const bool rn_same = cfg.rn_pos == cfg.rn_neg;
     const float shot_m1 = cfg.shot_inten_m1;
     // ---- time-step over the frames of the pack ---------------------------------------------
     for (int n = 1; n < T; ++n) {
-        const FrameSc& fs = prm.fr[seq][n];
-        const int st = use_ring ? (n - 1) % prm.stages : 0;
-        const unsigned char* s_frame = s_ring + (size_t)st * stage_bytes;
         if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 0] = clock64();
-        if (use_ring && ngroups > 0) mbar_wait(&s_bar[st], ((n - 1) / prm.stages) & 1);
+        if (use_ring && ngroups > 0) mbar_wait(&s_bar[0], (n - 1) & 1);
         if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 1] = clock64();
-        const float s_small = fs.s_small, s_large = fs.s_large, sdt = fs.sdt;
-        const float shot_k = shot_frame_k(fs.shot_c);
+        const FrameSc fs = s_fr[n];
 
         // ---- phase A: low-pass, leak, diff, count; flagged pixels go to the event queue ------
         int lmax = 0;
@@ -299,12 +374,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                 const int p0 = tile_px0 + gl * 4;
                 float4 x4;
                 if (use_ring) {
-                    if (FDT == V2E_DT_F32) x4 = *(const float4*)(s_frame + gl * 16);
+                    if (FDT == V2E_DT_F32) x4 = lds_f4(a_ring + gl * 16);
                     else if (FDT == V2E_DT_U8) {
-                        const uchar4 v = *(const uchar4*)(s_frame + gl * 4);
-                        x4 = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+                        const unsigned v = lds_u32(a_ring + gl * 4);
+                        x4 = make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu),
+                                         (float)((v >> 16) & 0xffu), (float)(v >> 24));
                     } else {
-                        const uint2 v = *(const uint2*)(s_frame + gl * 8);
+                        const uint2 v = lds_u2(a_ring + gl * 8);
                         x4 = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
                                          __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
                     }
@@ -312,7 +388,9 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     x4 = load_frame4<FDT>(sq.frames, (long long)n * P + p0);
                 }
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
+                float4 lk4 = make_float4(0, 0, 0, 0);
                 unsigned shot_bytes = 0;
+                if (leak) lk4 = lds_f4(a_lkn + gl * 16);
                 if (philox) {
                     const uint4 w = noise_words<R>(sq.philox_ctr, n, (unsigned)(g0 + gl), 0);
                     shot_bytes = w.z;
@@ -328,6 +406,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
                 }
                 const float* xp = &x4.x;
+                const float* lkp = &lk4.x;
                 unsigned ent[4];
                 unsigned gflags = 0;
                 signed char polb[4];
@@ -336,14 +415,14 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                 for (int e = 0; e < 4; ++e) {
                     const int j = g * 4 + e;
                     float L, I;
-                    log_inten(s_lut, xp[e], L, I);
+                    log_inten_s(a_lut, xp[e], L, I);
                     float nw = L;
                     if (cutoff) {
-                        const float s = (small_mask >> j) & 1u ? s_small : s_large;
+                        const float s = (small_mask >> j) & 1u ? fs.s_small : fs.s_large;
                         lpv[j] = lowpass(lpv[j], L, I, s);
                         nw = lpv[j];
                     }
-                    if (leak) base[j] = leak_sub(base[j], lkn[j], jit, z[e], sdt, pos[j]);
+                    if (leak) base[j] = leak_sub(base[j], lkp[e], jit, z[e], fs.sdt, pos[j]);
                     // diff / polarity / threshold (v2e_model.py:375,394-404), see diff_count()
                     const float diff = fsub(nw, base[j]);
                     const float ad = fabsf(diff);
@@ -356,8 +435,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     unsigned byte = 0;
                     if (shot) {
                         if (philox) {
-                            const float rn = rn_same ? cfg.rn_pos : (up ? cfg.rn_pos : cfg.rn_neg);
-                            thr256 = (shot_k * fmaf(shot_m1, I, 1.0f)) * (rn * C);   // 0 if !live
+                            thr256 = shot_thr256(up ? fs.kp : fs.kn, shot_m1, I, C);   // 0 if !live
                             byte = (shot_bytes >> (8 * e)) & 0xffu;
                             maybe = maybe || (float)byte < thr256;
                         } else {
@@ -367,29 +445,11 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     ent[e] = 0;
                     if (GENERIC) { polb[e] = live ? (up ? 1 : -1) : 0; cntb[e] = 0; }
                     if (__builtin_expect(maybe, 0)) {
-                        // rare path (~4 % of pixel-frames): exact count, shot second stage, queue
-                        const int cnt = cross ? count_div(ad, fadd(C, 1e-9f)) : 0;
-                        bool cand = false;
-                        if (shot && live) {
-                            if (philox) {
-                                if ((float)byte < thr256) {
-                                    const float u = shot_uniform<R>(sq.philox_ctr, n, p0 + e, byte);
-                                    cand = u * 256.0f < thr256;
-                                    if (cand) {
-                                        const int k = atomicAdd(s_ncand, 1);
-                                        if (k < kCandCap) s_cand[k] = CandEntry{gl * 4 + e, u};
-                                    }
-                                }
-                            } else {
-                                cand = true;
-                            }
-                        }
-                        if (cnt > 0 || cand) {
-                            gflags |= 1u << e;
-                            lmax = max(lmax, cnt);
-                            ent[e] = q_pack(gl * 4 + e, up, cand, cnt);
-                        }
-                        if (GENERIC) cntb[e] = cnt;
+                        const unsigned fl = (cross ? 1u : 0u) | (live ? 2u : 0u) | (up ? 4u : 0u) |
+                                            (shot ? 8u : 0u) | (philox ? 16u : 0u) | (byte << 8);
+                        ent[e] = rare_px<R>(&rctx, n, p0 + e, gl * 4 + e, ad, C, I, thr256, fl, &lmax);
+                        if (ent[e]) gflags |= 1u << e;
+                        if (GENERIC) cntb[e] = (int)(ent[e] >> 15);
                     }
                 }
                 if (gflags) {
@@ -430,17 +490,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                 if (tile == 0 && sq.max_iters) sq.max_iters[n] = mx;
             }
         } else if (tid == 32) {
-            // every thread is past its use of the previous frame's stage: refill it with the
-            // frame `stages` ahead (off the barrier's critical path)
-            if (use_ring && ngroups > 0 && n >= 2) {
-                const int nn = n - 1 + prm.stages;
-                if (nn < T) {
-                    const int st2 = (nn - 1) % prm.stages;
-                    mbar_expect_tx(&s_bar[st2], frame_bytes);
-                    tma_load_1d(s_ring + (size_t)st2 * stage_bytes,
-                                (const unsigned char*)sq.frames + ((size_t)nn * P + tile_px0) * prm.frame_elem,
-                                frame_bytes, &s_bar[st2]);
-                }
+            // every thread has consumed this frame's tile: fetch the next one (L2 -> smem) while
+            // the barrier is in flight
+            if (use_ring && ngroups > 0 && n + 1 < T) {
+                mbar_expect_tx(&s_bar[0], frame_bytes);
+                tma_load_1d(s_ring, (const unsigned char*)sq.frames +
+                                        ((size_t)(n + 1) * P + tile_px0) * prm.frame_elem,
+                            frame_bytes, &s_bar[0]);
             }
         }
         __syncthreads();
@@ -449,10 +505,13 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         // ---- phase B: the CTA drains the event queue, one entry per thread -------------------
         {
             const int qn = *s_qcount;
-            if (tid < qn) {
+            // entry q goes to lane q / kWarps of warp q % kWarps: every warp gets ~qn/kWarps
+            // entries, so no warp walks a long divergent iteration loop on the critical path
+            const int q0 = (tid & 31) * kWarps + (tid >> 5);
+            if (q0 < qn) {
                 const FrameGlobals g = frame_globals(*s_mx, sq.duration, sq.Tr);
                 const int ncand = min(*s_ncand, kCandCap);
-                for (int q = tid; q < qn; q += kPThreads) {
+                for (int q = q0; q < qn; q += kPThreads) {
                     const unsigned e = s_q[q];
                     const int lidx = (int)(e & 0x1fffu);
                     const bool up = (e >> 13) & 1u;
@@ -463,26 +522,28 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     int mode = 0;
                     if (cand && g.mx > 0) {   // rare: shot candidate (or injected shot draws)
                         mode = philox ? 2 : 1;
-                        C = up ? __ldg(sq.pos + p) : __ldg(sq.neg + p);
-                        const float x = use_ring ? ring_px<FDT>(s_frame, lidx)
-                                                 : load_frame1<FDT>(sq.frames, (long long)n * P + p);
-                        float L;
-                        log_inten(s_lut, x, L, I);
-                        if (philox) {
-                            bool found = false;
+                        bool found = false;
+                        if (philox)
                             for (int k = 0; k < ncand; ++k)
-                                if (s_cand[k].lidx == lidx) { u = s_cand[k].u; found = true; }
-                            if (!found) {   // candidate table overflowed: redraw (same value)
+                                if (s_cand[k].lidx == lidx) {
+                                    u = s_cand[k].u; I = s_cand[k].I; C = s_cand[k].C; found = true;
+                                }
+                        if (!found) {   // injected draws, or the candidate table overflowed
+                            C = up ? __ldg(sq.pos + p) : __ldg(sq.neg + p);
+                            float L;
+                            log_inten(s_lut, load_frame1<FDT>(sq.frames, (long long)n * P + p), L, I);
+                            if (philox) {   // redraw (same value as in phase A)
                                 const uint4 w = noise_words<R>(sq.philox_ctr, n, (unsigned)(p >> 2), 0);
                                 u = shot_uniform<R>(sq.philox_ctr, n, p, (w.z >> (8 * (p & 3))) & 0xffu);
                             }
                         }
                     }
                     float tm = s_tmem[lidx];
+                    float* vp = s_vox + lidx;
                     const float polf = up ? 1.f : -1.f;
                     const int fin = iterate_pixel<R>(
                         s_ctx->cfg, s_ctx->sq, fs, g, n, p, polf, C, cnt, I, tm, mode, u,
-                        [&](int b, float v) { s_vox[b * tile_px + lidx] = fadd(s_vox[b * tile_px + lidx], v); },
+                        [&](int b, float v) { vp[b * tile_px] = fadd(vp[b * tile_px], v); },
                         [&](float ts, float pl) {
                             const unsigned long long sl = atomicAdd(&wk.raw_count, 1ull);
                             if ((long long)sl < sq.raw_capacity) {
@@ -501,6 +562,7 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
         }
         if (tl && tid == 0) tl[((size_t)blockIdx.x * V2E_MAX_FRAMES + n) * 8 + 7] = clock64();
         __syncthreads();
+        if (tid == 0) { *s_qcount = 0; *s_ncand = 0; }   // nobody reads them until the next frame
         if (flags) {
             // memory update base += (pol*final)*C (v2e_model.py:522)
 #pragma unroll
@@ -518,7 +580,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
             }
         }
         __syncthreads();  // queue slots are reused by the next frame
-        if (tid == 0) { *s_qcount = 0; *s_ncand = 0; }
     }
 
     // ---- write back the dynamic state ----------------------------------------------------------
@@ -681,17 +742,12 @@ static PersistPlan make_plan(const CfgDev& cfg, int frame_dtype, int n_seq) {
     if (tg * 4 > kTileMaxPx) return pl;
     tiles = (total_groups + tg - 1) / tg;
     const bool tma_ok = ((size_t)cfg.P * fe) % 16 == 0;
-    // header + timestamp_mem + num_bins voxel planes + event queue (one word per pixel)
-    const size_t fixed = kHeaderBytes + (size_t)tg * 4 * sizeof(float) * (2 + cfg.nb);
-    int stages = 0;
-    if (tma_ok) {
-        const size_t sb = ((size_t)tg * 4 * fe + 127) & ~(size_t)127;
-        for (int s = kStagesMax; s >= 1; --s)
-            if (fixed + s * sb <= (size_t)g_smem_optin) { stages = s; break; }
-    }
-    if (stages == 1) stages = 0;  // the ring needs one frame of lead: 2+ stages or none
+    // header + timestamp_mem + leak plane + num_bins voxel planes + event queue (1 word / pixel)
+    const size_t fixed = kHeaderBytes + (size_t)tg * 4 * sizeof(float) * (3 + cfg.nb);
     const size_t sb = ((size_t)tg * 4 * fe + 127) & ~(size_t)127;
-    size_t smem = fixed + (size_t)stages * sb;
+    // one frame tile in flight: it is refilled (from L2) while the CTA sits in the frame barrier
+    const int stages = tma_ok ? 1 : 0;
+    const size_t smem = fixed + (size_t)stages * sb;
     if (smem > (size_t)g_smem_optin) return pl;
     pl.ok = 1;
     pl.tiles_per_seq = tiles;
@@ -748,7 +804,7 @@ static int run_persistent_t(const CfgDev& cfg, int rounds, const v2e_pack* packs
         fill_seq(prm.seq[s], packs[s]);
         for (int n = 1; n < packs[s].sc.num_frames; ++n) {
             const v2e_frame_scalars& f = packs[s].sc.fr[n];
-            prm.fr[s][n] = FrameSc{f.t_bin_prev, f.s_large, f.s_small, f.sdt, f.shot_c};
+            prm.fr[s][n] = make_frame_sc(cfg, f);
         }
         const v2e_pack& p = packs[s];
         dbg = dbg || p.dbg_pol || p.dbg_cnt || p.dbg_final || p.dbg_leak_randn || p.dbg_shot;

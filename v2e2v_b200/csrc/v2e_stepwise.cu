@@ -110,8 +110,7 @@ __global__ void __launch_bounds__(kThreads) k_phase_a(const __grid_constant__ St
             const int pol = (int)a.pol;
             int cand = 0;
             if (philox && shot && pol != 0) {
-                const float thr256 = shot_thr256(cfg, shot_frame_k(fs.shot_c), I, a.C,
-                                                 pol > 0 ? cfg.rn_pos : cfg.rn_neg);
+                const float thr256 = shot_thr256(pol > 0 ? fs.kp : fs.kn, cfg.shot_inten_m1, I, a.C);
                 const unsigned byte = (w.z >> (8 * e)) & 0xffu;
                 if ((float)byte < thr256)
                     cand = shot_uniform<R>(sq.philox_ctr, n, p, byte) * 256.0f < thr256;
@@ -307,7 +306,7 @@ static int run_stepwise_t(const CfgDev& cfg, const v2e_pack* packs, int n_seq, v
         prm.n = n;
         for (int s = 0; s < n_seq; ++s) {
             const v2e_frame_scalars& f = packs[s].sc.fr[n];
-            prm.fr[s] = FrameSc{f.t_bin_prev, f.s_large, f.s_small, f.sdt, f.shot_c};
+            prm.fr[s] = make_frame_sc(cfg, f);
         }
         // sequences with fewer frames than T are not supported in one launch (checked by caller)
         k_phase_a<FDT, R><<<grid_g4, kThreads, 0, st>>>(prm);
