@@ -172,45 +172,6 @@ __device__ __forceinline__ void log_inten_s(unsigned lut_addr, float x, float& L
 }
 
 
-// Rare per-pixel path of phase A (~4 % of pixel-frames), out of line to keep the streaming loop
-// small: exact event count on a threshold crossing, second stage of the PHILOX shot test, and the
-// queue entry.  Returns the packed entry (0 = nothing to do) and raises lmax.
-struct RareCtx {
-    unsigned long long philox_ctr;
-    int* s_ncand;
-    CandEntry* s_cand;
-};
-template <int R>
-static __device__ __noinline__ unsigned rare_px(const RareCtx* rc, int n, int p, int lidx, float ad,
-                                                float C, float I, float thr256, unsigned flags_in,
-                                                int* lmax) {
-    // flags_in: bit0 cross, bit1 live, bit2 up, bit3 shot on, bit4 philox, bits 8..15 shot byte
-    const bool cross = flags_in & 1u, live = flags_in & 2u, up = flags_in & 4u;
-    const bool shot = flags_in & 8u, philox = flags_in & 16u;
-    const unsigned byte = (flags_in >> 8) & 0xffu;
-    const int cnt = cross ? count_div(ad, fadd(C, 1e-9f)) : 0;
-    bool cand = false;
-    if (shot && live) {
-        if (philox) {
-            if ((float)byte < thr256) {
-                const float u = shot_uniform<R>(rc->philox_ctr, n, p, byte);
-                cand = u * 256.0f < thr256;
-                if (cand) {
-                    const int k = atomicAdd(rc->s_ncand, 1);
-                    if (k < kCandCap) rc->s_cand[k] = CandEntry{lidx, u, I, C};
-                }
-            }
-        } else {
-            cand = true;  // injected draws: every pol != 0 pixel walks its iterations
-        }
-    }
-    if (cnt > 0 || cand) {
-        *lmax = max(*lmax, cnt);
-        return q_pack(lidx, up, cand, cnt);
-    }
-    return 0u;
-}
-
 // NOISE: 0 = no noise, 1 = PHILOX leak + shot (the V2E2VNet wiring), 2 = generic: every feature
 // flag is read at run time, debug outputs and injected noise are honoured (tests, odd configs).
 template <int FDT, int R, int NOISE, bool CUTOFF>
@@ -352,7 +313,6 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
     __syncthreads();
 
     long long nev = 0;
-    RareCtx rctx{sq.philox_ctr, s_ncand, s_cand};
     const float jit = cfg.leak_jitter;
     const float shot_m1 = cfg.shot_inten_m1;
     // ---- time-step over the frames of the pack ---------------------------------------------
@@ -445,11 +405,29 @@ __global__ void __launch_bounds__(kPThreads, 1) k_persistent(const __grid_consta
                     ent[e] = 0;
                     if (GENERIC) { polb[e] = live ? (up ? 1 : -1) : 0; cntb[e] = 0; }
                     if (__builtin_expect(maybe, 0)) {
-                        const unsigned fl = (cross ? 1u : 0u) | (live ? 2u : 0u) | (up ? 4u : 0u) |
-                                            (shot ? 8u : 0u) | (philox ? 16u : 0u) | (byte << 8);
-                        ent[e] = rare_px<R>(&rctx, n, p0 + e, gl * 4 + e, ad, C, I, thr256, fl, &lmax);
-                        if (ent[e]) gflags |= 1u << e;
-                        if (GENERIC) cntb[e] = (int)(ent[e] >> 15);
+                        // rare path (~4 % of pixel-frames): exact count, shot second stage, queue
+                        const int cnt = cross ? count_div(ad, fadd(C, 1e-9f)) : 0;
+                        bool cand = false;
+                        if (shot && live) {
+                            if (philox) {
+                                if ((float)byte < thr256) {
+                                    const float u = shot_uniform<R>(sq.philox_ctr, n, p0 + e, byte);
+                                    cand = u * 256.0f < thr256;
+                                    if (cand) {
+                                        const int k = atomicAdd(s_ncand, 1);
+                                        if (k < kCandCap) s_cand[k] = CandEntry{gl * 4 + e, u, I, C};
+                                    }
+                                }
+                            } else {
+                                cand = true;
+                            }
+                        }
+                        if (cnt > 0 || cand) {
+                            gflags |= 1u << e;
+                            lmax = max(lmax, cnt);
+                            ent[e] = q_pack(gl * 4 + e, up, cand, cnt);
+                        }
+                        if (GENERIC) cntb[e] = cnt;
                     }
                 }
                 if (gflags) {
