@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define V2E_ABI_VERSION 1
+#define V2E_ABI_VERSION 2
 
 #define V2E_MAX_FRAMES 32   /* max frames per pack (num_pack_frames); reference default is 10 */
 #define V2E_MAX_BINS 8      /* max voxel bins; reference default is 5                        */
@@ -53,6 +53,11 @@ extern "C" {
 #define V2E_ERR_CUDA (-4)           /* a CUDA runtime call failed; see v2e_last_cuda_error      */
 #define V2E_ERR_WORKSPACE (-5)      /* workspace too small                                      */
 #define V2E_ERR_NO_DEVICE (-6)      /* no sm_100 device                                         */
+
+/* v2e_pack.status values written by the device */
+#define V2E_STATUS_OK 0
+#define V2E_STATUS_NONINTEGER_FRAMES 1 /* frames_integer was asserted but a value was not 0..255
+                                          integer: the outputs of this pack are invalid          */
 
 /* noise_mode */
 #define V2E_NOISE_OFF 0       /* leak_rate_hz == 0 and shot_noise_rate_hz == 0                   */
@@ -72,7 +77,9 @@ extern "C" {
 /* engine selection for v2e_pack_forward */
 #define V2E_ENGINE_AUTO 0
 #define V2E_ENGINE_STEPWISE 1   /* two launches per frame, state in HBM/L2; any size             */
-#define V2E_ENGINE_PERSISTENT 2 /* one cooperative launch per pack, state on chip                */
+#define V2E_ENGINE_PERSISTENT 2 /* one cooperative launch per pack, state on chip, lock-step     */
+#define V2E_ENGINE_RUNAHEAD 3   /* one cooperative launch per pack, streaming decoupled from the
+                                   per-frame max: only the pixels that fire wait for it          */
 
 /* Per-emulator static configuration (v2e/v2e_model.py:36-153). */
 typedef struct v2e_config {
@@ -93,6 +100,12 @@ typedef struct v2e_config {
     float rn_neg;            /* f32(1/neg_thres_nominal)   v2e_model.py:218                      */
     float shot_inten_m1;     /* f32(SHOT_NOISE_INTEN_FACTOR-1) emulator_utils.py:175             */
     int32_t philox_rounds;   /* 7 or 10 (0 -> default 10)                                        */
+    int32_t frames_integer;  /* 1: the caller guarantees integer-valued frames in 0..255 (what
+                                every reader of the reference produces; always true for
+                                V2E_DT_U8).  Lets the run-ahead engine drop the fp64 lin_log path
+                                from its streaming loop; a violation is detected and reported
+                                through v2e_pack.status, never served silently.               */
+    int32_t reserved_cfg;
     const float* lut;        /* device, [2][256]: lin_log(v), (v+20)/275 for v = 0..255          */
 } v2e_config;
 
@@ -129,6 +142,7 @@ typedef struct v2e_pack {
     float* raw_events;        /* device out [raw_capacity,5] rows t,x,y,pol,b (raw mode)         */
     int64_t raw_capacity;
     int64_t* num_events;      /* device out, scalar (also = rows written in raw mode)            */
+    int32_t* status;          /* device out, optional scalar: 0 ok, V2E_STATUS_NONINTEGER_FRAMES  */
     int32_t* max_iters;       /* device out [T] optional: per-frame max event count (n>=1)       */
     const float* leak_randn;  /* device [T-1,P]  injected randn (emulator_utils.py:113)          */
     const float* shot_rand;   /* device [T-1,shot_imax,P] injected rand (emulator_utils.py:191)  */

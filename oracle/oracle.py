@@ -40,8 +40,7 @@ def build(force: bool = False) -> str:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()   # no-op unless the source or the ABI header is newer than the library
         h = C.CDLL(_LIB_PATH)
         h.v2e_oracle_pack.restype = C.c_int
         h.v2e_oracle_pack.argtypes = [C.POINTER(_cabi.Config), C.POINTER(_cabi.Pack), C.c_int]

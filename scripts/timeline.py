@@ -22,7 +22,7 @@ off = (( _cabi.lib().v2e_workspace_bytes.__self__ is None) and 0) if False else 
 import ctypes
 ws = em._workspace
 # SeqWork size rounded to 256
-swork = 4*32 + 4*36 + 8 + 8 + 4 + 4 + 8*3*2048
+swork = 8 * 36 + 8 + 8 + 4 + 4 + 8 * 3 * 2048 + 4 * 32 * 160 + 8 * 4 * 160
 vox_off = (swork + 255) & ~255
 tl = ws[vox_off:vox_off + 148*32*8*8].view(torch.int64).cpu().numpy().reshape(148, 32, 8)
 tl = tl[:, 1:T, :]

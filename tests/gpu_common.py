@@ -7,7 +7,7 @@ import torch
 from oracle.oracle import OracleEmulator
 from tests.refharness import noise_arrays, synth_walk_pack, stamps
 
-ENGINES = ("stepwise", "persistent")
+ENGINES = ("stepwise", "persistent", "runahead")
 
 SD = dict(pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)
 CFG2 = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, sigma_thres=0.03,

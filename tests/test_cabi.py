@@ -87,7 +87,8 @@ def test_constants_match_header():
     for k in ("OK", "ERR_BAD_ARG", "ERR_UNSUPPORTED", "ERR_TIME_ORDER", "ERR_CUDA",
               "ERR_WORKSPACE", "ERR_NO_DEVICE", "NOISE_OFF", "NOISE_INJECTED", "NOISE_PHILOX",
               "DT_F32", "DT_U8", "DT_BF16", "OUT_VOXEL", "OUT_RAW", "OUT_VOXEL_UNNORM",
-              "ENGINE_AUTO", "ENGINE_STEPWISE", "ENGINE_PERSISTENT"):
+              "ENGINE_AUTO", "ENGINE_STEPWISE", "ENGINE_PERSISTENT",
+              "ENGINE_RUNAHEAD"):
         assert int(defs["V2E_" + k]) == getattr(_cabi, k), k
 
 

@@ -27,6 +27,8 @@ def _to_cuda_frames(frames_u8, dtype=torch.float32):
 def test_golden_reference_outputs(name, engine):
     """CUDA path vs outputs of the unmodified reference (tests/golden)."""
     g = GoldenCase(name)
+    if g.raw and engine == "runahead":
+        pytest.skip("the run-ahead engine serves the voxel modes only (raw -> persistent/stepwise)")
     em = gc.cuda_emulator(g.emu, engine)
     pos, neg, nra = g.planes()
     shp = (g.H, g.W)
@@ -115,7 +117,7 @@ def test_philox_mode_is_consistent_with_oracle(engine, rounds):
 
 
 def test_engines_agree_philox():
-    """Same seed/offset => stepwise and persistent engines draw identical noise."""
+    """Same seed/offset => all engines draw identical noise."""
     cfg, H, W, T = gc.CFG2, 64, 96, 10
     pos, neg, nra = gc.make_planes(13, H, W, cfg)
     outs = []
@@ -129,10 +131,11 @@ def test_engines_agree_philox():
             ev, nev = em(fr.to("cuda"), tfr)
             res.append((ev.cpu().numpy(), nev, em.base_log_frame.cpu().numpy().copy()))
         outs.append(res)
-    for a, b in zip(*outs):
-        assert a[1] == b[1]
-        np.testing.assert_array_equal(a[2], b[2])
-        np.testing.assert_allclose(a[0], b[0], rtol=VOX_RTOL, atol=VOX_ATOL)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert a[1] == b[1]
+            np.testing.assert_array_equal(a[2], b[2])
+            np.testing.assert_allclose(a[0], b[0], rtol=VOX_RTOL, atol=VOX_ATOL)
 
 
 def test_shot_noise_rate_statistics():

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 import threading
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_FRAMES = 32
 MAX_BINS = 8
 MAX_SEQ_PER_LAUNCH = 16
@@ -26,7 +26,7 @@ ERR_NO_DEVICE = -6
 NOISE_OFF, NOISE_INJECTED, NOISE_PHILOX = 0, 1, 2
 DT_F32, DT_U8, DT_BF16 = 0, 1, 2
 OUT_VOXEL, OUT_RAW, OUT_VOXEL_UNNORM = 0, 1, 2
-ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_PERSISTENT = 0, 1, 2
+ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_PERSISTENT, ENGINE_RUNAHEAD = 0, 1, 2, 3
 
 
 class Config(C.Structure):
@@ -50,6 +50,8 @@ class Config(C.Structure):
         ("rn_neg", C.c_float),
         ("shot_inten_m1", C.c_float),
         ("philox_rounds", C.c_int32),
+        ("frames_integer", C.c_int32),
+        ("reserved_cfg", C.c_int32),
         ("lut", C.c_void_p),
     ]
 
@@ -94,6 +96,7 @@ class Pack(C.Structure):
         ("raw_events", C.c_void_p),
         ("raw_capacity", C.c_int64),
         ("num_events", C.c_void_p),
+        ("status", C.c_void_p),
         ("max_iters", C.c_void_p),
         ("leak_randn", C.c_void_p),
         ("shot_rand", C.c_void_p),

@@ -40,6 +40,7 @@ static int make_cfg(const v2e_config* c, CfgDev& d) {
     d.noise_mode = c->noise_mode;
     d.output_mode = c->output_mode;
     d.voxel_bf16 = c->voxel_dtype == V2E_DT_BF16;
+    d.frames_integer = c->frames_integer != 0 || c->frame_dtype == V2E_DT_U8;
     d.leak_rate = c->leak_rate;
     d.leak_jitter = c->leak_jitter;
     d.rn_pos = c->rn_pos;
@@ -111,6 +112,13 @@ int v2e_resolve_engine(const v2e_config* c, int n_seq) {
     if (rc != V2E_OK) return rc;
     if (n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH) return V2E_ERR_BAD_ARG;
     if (c->engine == V2E_ENGINE_STEPWISE) return V2E_ENGINE_STEPWISE;
+    if (c->engine < V2E_ENGINE_AUTO || c->engine > V2E_ENGINE_RUNAHEAD) return V2E_ERR_BAD_ARG;
+    if (c->engine != V2E_ENGINE_PERSISTENT) {
+        const int ra = runahead_fits(cfg, c->frame_dtype, n_seq);
+        if (ra < 0) return ra;
+        if (ra) return V2E_ENGINE_RUNAHEAD;
+        if (c->engine == V2E_ENGINE_RUNAHEAD) return V2E_ERR_UNSUPPORTED;
+    }
     const int fits = persistent_fits(cfg, c->frame_dtype, n_seq);
     if (fits < 0) return fits;
     if (c->engine == V2E_ENGINE_PERSISTENT) return fits ? V2E_ENGINE_PERSISTENT : V2E_ERR_UNSUPPORTED;
@@ -133,6 +141,8 @@ int v2e_pack_forward(const v2e_config* c, const v2e_pack* packs, int n_seq, void
     const int engine = v2e_resolve_engine(c, n_seq);
     if (engine < 0) return engine;
     cudaStream_t st = (cudaStream_t)stream;
+    if (engine == V2E_ENGINE_RUNAHEAD)
+        return run_runahead(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
     if (engine == V2E_ENGINE_PERSISTENT)
         return run_persistent(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
     return run_stepwise(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);

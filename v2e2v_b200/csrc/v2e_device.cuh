@@ -27,6 +27,7 @@ struct SeqDev {
     float* raw_events;
     long long raw_capacity;
     unsigned long long* num_events;
+    int* status;
     int* max_iters;
     const float* leak_randn;
     const float* shot_rand;
@@ -55,6 +56,7 @@ struct CfgDev {
     int H, W, P, nb;
     int cutoff_on, leak_on, shot_on, noise_mode;
     int output_mode, voxel_bf16;
+    int frames_integer;
     float leak_rate, leak_jitter, rn_pos, rn_neg, shot_inten_m1;
     const float* lut;
 };
@@ -278,12 +280,65 @@ __device__ __forceinline__ FrameGlobals frame_globals(int mx, float duration, fl
 // Returns final_evts_frame for this pixel (post-refractory event count incl. shot events).
 //   pol/C/cnt: phase-A results; tm: timestamp_mem (updated in place)
 //   shot_mode: 0 none, 1 injected (reads sq.shot_rand), 2 philox candidate with uniform u
+// First iteration i in [i0, cnt) that the refractory gate accepts, i.e. with
+// fsub(ts_i, tm) > Tr where ts_i = fadd(t0, fmul(step, i+1)); cnt if there is none.  Every
+// operation is monotone non-decreasing in i, so the accepted iterations form a suffix and the
+// answer can be bracketed from an estimate instead of walking all refused iterations; the
+// predicate itself is evaluated exactly as the reference does (v2e_model.py:419,469).
+static __device__ __noinline__ int first_accept(int i0, int cnt, float t0, float step, float tm,
+                                                float Tr) {
+    auto pred = [&](int i) { return fsub(fadd(t0, fmul(step, (float)(i + 1))), tm) > Tr; };
+    if (pred(i0)) return i0;
+    if (!pred(cnt - 1)) return cnt;
+    int lo = i0, hi = cnt - 1;  // pred(lo) is false, pred(hi) is true
+    const int est = (int)__fdividef(fsub(fadd(Tr, tm), t0), step);  // ~ (i+1) at the threshold
+#pragma unroll 1
+    for (int k = est - 2; k <= est + 1; ++k) {
+        if (k <= lo) continue;
+        if (k >= hi) break;
+        if (pred(k)) { hi = k; break; }
+        lo = k;
+    }
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pred(mid)) hi = mid;
+        else lo = mid;
+    }
+    return hi;
+}
+
 template <int R, class VoxAdd, class Emit>
 __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq, const FrameSc& fs,
                                              const FrameGlobals& g, int n, int p, float pol,
                                              float C, int cnt, float I, float& tm, int shot_mode,
                                              float u, VoxAdd vox_add, Emit emit) {
     int final_cnt = 0;
+    if (shot_mode == 0 && g.gate) {
+        // no shot noise at this pixel and the gate is on (v2e_model.py:469): iterations [0,cnt)
+        // all carry an event, the gate refuses most of them.  Jump over the refused ones.
+        int i = 0;
+        while (i < cnt) {
+            if (cnt - i > 3) {
+                i = first_accept(i, cnt, fs.t_bin_prev, g.ts_step, tm, sq.Tr);
+                if (i >= cnt) break;
+            }
+            const float ts = fadd(fs.t_bin_prev, fmul(g.ts_step, (float)(i + 1)));
+            ++i;
+            if (!(fsub(ts, tm) > sq.Tr)) continue;
+            tm = ts;
+            final_cnt += 1;
+            if (cfg.output_mode == V2E_OUT_RAW) {
+                emit(ts, pol);
+            } else {  // v2e_model.py:478-502
+                const float ti = floorf(ts);
+                const float d = fsub(ts, ti);
+                const int b = (int)ti;
+                if (b >= 0 && b < cfg.nb) vox_add(b, fmul(pol, fsub(1.0f, d)));
+                if (b >= 0 && b + 1 < cfg.nb) vox_add(b + 1, fmul(pol, d));
+            }
+        }
+        return final_cnt;
+    }
     int last = cnt;  // iterations [0,last) can produce events
     double thr64 = 0.;
     float thr32 = 0.f, p_it = 0.f;

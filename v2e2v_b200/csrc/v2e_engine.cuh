@@ -9,6 +9,7 @@
 namespace v2e {
 
 constexpr int kMaxPartials = 2048;
+constexpr int kRaMaxTiles = 160;  // run-ahead engine: tiles (CTAs) per sequence, <= SM count
 
 // Per-sequence work area inside the caller's workspace.  Zero on entry, zero on exit.
 struct SeqWork {
@@ -20,6 +21,10 @@ struct SeqWork {
     unsigned exit_count;                  // persistent engine: CTAs that left (last one cleans)
     unsigned pad;
     double partials[3 * kMaxPartials];    // per-CTA (sum, sum of squares, nnz)
+    // run-ahead engine: flag-free grid barriers.  slot[n][tile] = (tile max of frame n) + 1 and
+    // stat[tile][k] = ~bits of (sum, sum of squares, nnz, events); 0 means "not arrived yet".
+    unsigned ra_slot[V2E_MAX_FRAMES * kRaMaxTiles];
+    unsigned long long ra_stat[4 * kRaMaxTiles];
 };
 using StepWork = SeqWork;
 
@@ -62,6 +67,7 @@ inline void fill_seq(SeqDev& d, const v2e_pack& p) {
     d.raw_events = p.raw_events;
     d.raw_capacity = p.raw_capacity;
     d.num_events = (unsigned long long*)p.num_events;
+    d.status = p.status;
     d.max_iters = p.max_iters;
     d.leak_randn = p.leak_randn;
     d.shot_rand = p.shot_rand;
@@ -103,7 +109,10 @@ int run_stepwise(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack*
                  void* workspace, cudaStream_t st);
 int run_persistent(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs,
                    int n_seq, void* workspace, cudaStream_t st);
-// 1 if the persistent engine can hold n_seq sequences of this config on chip on this device
+int run_runahead(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs, int n_seq,
+                 void* workspace, cudaStream_t st);
+// 1 if the persistent / run-ahead engine can hold n_seq sequences of this config on chip
 int persistent_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
+int runahead_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
 
 }  // namespace v2e

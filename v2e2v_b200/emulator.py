@@ -94,7 +94,7 @@ class EventEmulator(nn.Module):
             device="cuda",
             # ---- extensions (keyword-only in spirit; defaults keep the reference behaviour) ----
             noise_mode: Optional[str] = None,     # 'philox' | 'injected' | 'off'
-            engine: str = "auto",                 # 'auto' | 'persistent' | 'stepwise'
+            engine: str = "auto",                 # 'auto' | 'runahead' | 'persistent' | 'stepwise'
             voxel_dtype: torch.dtype = torch.float32,
             philox_rounds: int = 10,
             normalize: bool = True,
@@ -246,7 +246,8 @@ class EventEmulator(nn.Module):
         else:
             cfg.output_mode = _cabi.OUT_VOXEL if self.normalize else _cabi.OUT_VOXEL_UNNORM
         cfg.engine = {"auto": _cabi.ENGINE_AUTO, "stepwise": _cabi.ENGINE_STEPWISE,
-                      "persistent": _cabi.ENGINE_PERSISTENT}[self.engine]
+                      "persistent": _cabi.ENGINE_PERSISTENT,
+                      "runahead": _cabi.ENGINE_RUNAHEAD}[self.engine]
         f32 = torch.float32
         cfg.leak_rate = float(torch.tensor(self.leak_rate_hz, dtype=f32))
         cfg.leak_jitter = float(torch.tensor(self.leak_jitter_fraction, dtype=f32))
@@ -275,7 +276,8 @@ class EventEmulator(nn.Module):
         if self._launch is None:
             return None
         return {_cabi.ENGINE_STEPWISE: "stepwise",
-                _cabi.ENGINE_PERSISTENT: "persistent"}.get(self._launch.resolve_engine())
+                _cabi.ENGINE_PERSISTENT: "persistent",
+                _cabi.ENGINE_RUNAHEAD: "runahead"}.get(self._launch.resolve_engine())
 
     def forward(self, frames, t_frames):
         """Compute events based on a sequence of frames (v2e_model.py:290-536).
