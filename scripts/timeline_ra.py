@@ -32,9 +32,10 @@ stat("stream: frame1 done (from start)", fr[:, 0, 0] - t0[:, 0])
 stat("stream: per-frame period", np.diff(fr[:, :, 0], axis=1))
 stat("stream: last frame done", fr[:, -1, 0] - t0[:, 0])
 stat("resolve: wait grid barrier", fr[:, :, 4] - fr[:, :, 1])
-stat("resolve: events + next frame", fr[:, :, 5] - fr[:, :, 4])
-stat("resolve: sync + arrive", fr[:, :, 3] - fr[:, :, 5])
-stat("resolve: list+load+tail", fr[:, :, 6] - fr[:, :, 3])
+stat("resolve: release -> arrive", fr[:, :, 3] - fr[:, :, 4])
+stat("   slowest tail (per CTA)", fr[:, :, 2])
+stat("   slowest events+step (per CTA)", fr[:, :, 5])
+stat("resolve: list+load", fr[:, :, 6] - fr[:, :, 3])
 stat("resolve: round period", np.diff(fr[:, :, 1], axis=1))
 stat("resolve: list length", fr[:, :, 7])
 stat("roles done (from start)", tl[:, 0, 2] - t0[:, 0])
@@ -44,4 +45,13 @@ stat("normalise+store", tl[:, 0, 5] - tl[:, 0, 4])
 stat("total", tl[:, 0, 5] - t0[:, 0])
 for n in range(1, T):
     f = lambda k: np.median(tl[:, n, k] - t0[:, 0])
-    print(f"  round {n}: start {f(1):8.0f} released {f(4):8.0f} events {f(5):8.0f} arrived {f(3):8.0f} tail {f(6):8.0f} | stream done {f(0):8.0f}  list {np.median(tl[:, n, 7]):5.0f}")
+    print(f"  round {n}: start {f(1):8.0f} released {f(4):8.0f} arrived {f(3):8.0f} listed {f(6):8.0f} | max tail {np.median(tl[:, n, 2]):6.0f} max ev {np.median(tl[:, n, 5]):6.0f} (worst CTA {tl[:, n, 2].max():6.0f} {tl[:, n, 5].max():6.0f}) | stream done {f(0):8.0f}  list {np.median(tl[:, n, 7]):5.0f}")
+
+for n in range(1, T):
+    x = tl[:, n + 16, :3]
+    print(f"  round {n}: slowest thread per CTA (median over CTAs / worst): entry-load wait {np.median(x[:,0]):6.0f}/{x[:,0].max():6.0f}  events {np.median(x[:,1]):6.0f}/{x[:,1].max():6.0f}  step {np.median(x[:,2]):6.0f}/{x[:,2].max():6.0f}")
+
+for n in range(1, T):
+    x = tl[:, n + 16, :]
+    k = int(np.argmax(x[:, 3]))
+    print(f"  round {n}: slowest do_events over the chip: total {x[k,3]:6.0f} = fetch+load-wait {x[k,4]:6.0f} + diff_count {x[k,5]:6.0f} + iterate/stores {x[k,6]:6.0f}; cnt*1000+fin {x[k,7]:6.0f} | median CTA: {np.median(x[:,3]):6.0f} = {np.median(x[:,4]):6.0f} + {np.median(x[:,5]):6.0f} + {np.median(x[:,6]):6.0f}")

@@ -230,3 +230,33 @@ def test_non_integer_frames_slow_path():
             ov, onev = orc.forward(fr.numpy(), tfr)
             assert nev == onev
             gc.assert_state_equal(em, orc, True)
+
+
+def test_runahead_integer_frames_contract():
+    """integer_frames=True selects the run-ahead variant without the fp64 lin_log path: same
+    results on integer-valued frames, and a violation is detected and raised, never served."""
+    cfg = dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0)
+    H, W, T = 64, 96, 10
+    pos, neg, _ = gc.make_planes(7, H, W, cfg)
+    em = gc.cuda_emulator(cfg, "runahead", integer_frames=True)
+    orc = OracleEmulator(**cfg)
+    em.set_planes(pos, neg)
+    orc.set_planes(pos, neg)
+    last = None
+    for k, fr, tfr in gc.video(4, 3, T, H, W):
+        ev, nev = em(fr.cuda(), tfr)
+        ov, onev = orc.forward(fr.numpy(), tfr)
+        assert nev == onev
+        gc.assert_state_equal(em, orc, True, f"pack {k}")
+        np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+        last = fr
+    bad = last.clone()
+    bad[0, 3, 5, 7] += 0.25
+    with pytest.raises(ValueError, match="not an integer"):
+        em(bad.cuda(), gc.stamps(3, T, 1000.0))
+
+
+def test_auto_engine_is_fastest_known():
+    em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
+    em(torch.zeros(1, 4, 64, 64, device="cuda"), torch.tensor([[0.0, 0.003]], dtype=torch.float64))
+    assert em.resolved_engine == "persistent"

@@ -113,15 +113,20 @@ int v2e_resolve_engine(const v2e_config* c, int n_seq) {
     if (n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH) return V2E_ERR_BAD_ARG;
     if (c->engine == V2E_ENGINE_STEPWISE) return V2E_ENGINE_STEPWISE;
     if (c->engine < V2E_ENGINE_AUTO || c->engine > V2E_ENGINE_RUNAHEAD) return V2E_ERR_BAD_ARG;
-    if (c->engine != V2E_ENGINE_PERSISTENT) {
+    if (c->engine == V2E_ENGINE_RUNAHEAD) {
         const int ra = runahead_fits(cfg, c->frame_dtype, n_seq);
         if (ra < 0) return ra;
-        if (ra) return V2E_ENGINE_RUNAHEAD;
-        if (c->engine == V2E_ENGINE_RUNAHEAD) return V2E_ERR_UNSUPPORTED;
+        return ra ? V2E_ENGINE_RUNAHEAD : V2E_ERR_UNSUPPORTED;
     }
+    // AUTO: the lock-step persistent engine is the faster one on B200 today (DESIGN.md,
+    // "Engines"); the run-ahead engine is opt-in.
     const int fits = persistent_fits(cfg, c->frame_dtype, n_seq);
     if (fits < 0) return fits;
     if (c->engine == V2E_ENGINE_PERSISTENT) return fits ? V2E_ENGINE_PERSISTENT : V2E_ERR_UNSUPPORTED;
+    if (!fits && cfg.output_mode != V2E_OUT_RAW) {
+        const int ra = runahead_fits(cfg, c->frame_dtype, n_seq);
+        if (ra > 0) return V2E_ENGINE_RUNAHEAD;
+    }
     return fits ? V2E_ENGINE_PERSISTENT : V2E_ENGINE_STEPWISE;
 }
 

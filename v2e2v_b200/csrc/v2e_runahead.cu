@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     const bool is_stream = warp < kRaStreamWarps;
     const int ts = tid;  // stream thread index (stream warps come first)
     long long* tl = prm.timeline ? prm.timeline + (size_t)blockIdx.x * V2E_MAX_FRAMES * 8 : nullptr;
-    if (tl && tid == 0) tl[0] = clock64();
+    if (tl && tid == 0) {
+        tl[0] = clock64();
+        for (int n = 1; n < V2E_MAX_FRAMES; ++n) tl[n * 8 + 2] = tl[n * 8 + 5] = 0;
+        for (int n = 16 * 8; n < V2E_MAX_FRAMES * 8; ++n) tl[n] = 0;
+    }
 
     // ---- stream threads: issue the loads of the per-pixel planes before anything else ----------
     float4 ld_pos[kRaGroups], ld_neg[kRaGroups], ld_nra[kRaGroups], ld_b[kRaGroups],
@@ -362,9 +366,13 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     // frame n: the events of a parked pixel (v2e_model.py:449-522)
     auto do_events = [&](RaEntry& e, int n, const FrameSc& fs, const FrameGlobals& fg) {
         const int p = tile_px0 + e.lidx;
+        const long long c0 = tl ? clock64() : 0;
         float L, I;
         fetch_li(e, n, L, I);
+        long long c1 = 0, c2 = 0;
+        if (tl) { asm volatile("" ::"f"(L), "f"(e.b), "f"(e.l), "f"(e.tm)); c1 = clock64(); }
         const PixelA a = diff_count(cutoff ? e.l : L, e.b, s_pos[slot_of(e.lidx)], s_neg[slot_of(e.lidx)]);
+        if (tl) { asm volatile("" ::"f"(a.C), "r"(a.cnt)); c2 = clock64(); }
         int mode = 0;
         float u = 0.f;
         if (shot && a.pol != 0.f && fg.mx > 0) {
@@ -387,6 +395,14 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             e.b = fadd(e.b, fmul(fmul(a.pol, (float)fin), a.C));  // memory update (:522)
             nev += fin;
             if (GENERIC && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
+        }
+        if (tl && n + 16 < V2E_MAX_FRAMES) {
+            const long long c3 = clock64();
+            unsigned long long* x = (unsigned long long*)&tl[(n + 16) * 8];
+            const unsigned long long tot = (unsigned long long)(c3 - c0);
+            if (atomicMax(x + 3, tot) < tot) {
+                x[4] = c1 - c0; x[5] = c2 - c1; x[6] = c3 - c2; x[7] = a.cnt * 1000 + fin;
+            }
         }
     };
     // frame m without events: low-pass, leak, diff.  Returns true if the pixel fires (or is a
@@ -760,8 +776,20 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         bool phase1 = !is_stream;
         int n_first = 1;
         int ln = 0;
-        RaEntry cur, nxt;
-        cur.lidx = nxt.lidx = -1;
+        // Phase 2 has four times more threads than a round has parked pixels: consecutive rounds
+        // use disjoint quarters of the threads, so that the thread that carries a pixel of round
+        // n on through n+2.. (the "tail") is not the one that serves a pixel of round n+1.
+        auto slot_in_round = [&](int n) {
+            if (phase1) return rt;
+            // warps of one parity serve the parked pixels of even rounds, the others those of odd
+            // rounds: list slot = (index of my warp among its parity) * 32 + lane
+            const int w = rt >> 5;
+            return ((w ^ n) & 1) ? (1 << 20) : (((w >> 1) << 5) | (rt & 31));
+        };
+        const int nslots2 = ((kRaThreads / 32 + 1) / 2) * 32;  // list slots served per round in phase 2
+        RaEntry cur, tle;   // my pixel of this round; my pixel of the last round still to carry on
+        int tle_m = 0;      // ... from this frame on
+        cur.lidx = tle.lidx = -1;
         if (is_stream) {
             if (tl && tid == 0) tl[2] = clock64();
             ra_named_sync(2, kRaThreads);  // meets the resolve warps at their hand-over
@@ -771,11 +799,11 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             bar = 2;
             if (n_first < T) {
                 ln = ra_lds_volatile(&ctl->listn[n_first & 1]);
-                if (rt < ln) load_entry(cur, s_list[rt], n_first);
+                const int q = slot_in_round(n_first);
+                if (q < ln) load_entry(cur, s_list[q], n_first);
             }
         } else if (T > 1) {
             if (rt == 0) arrive(1);
-            ra_named_sync(1, kRaResolveThreads);
             build_list(1, rt, nrt);
             ra_named_sync(1, kRaResolveThreads);
             ln = ra_lds_volatile(&ctl->listn[1]);
@@ -810,17 +838,51 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             const FrameGlobals fg = frame_globals(ra_lds_volatile(&ctl->mx), sq.duration, sq.Tr);
             const FrameSc fs = s_fr[n];
 
+            // ---- the pixel I still carry from the last round: on through its frames until it fires
+            //      again (re-park) or the pack ends.  Its park byte must be in place before the
+            //      list of frame n+1 is built, i.e. before the barrier below. ------------------------
+            const long long t_a = tl ? clock64() : 0;
+            if (tle.lidx >= 0) {
+                int m = tle_m, c = 0;
+                for (; m < T; ++m)
+                    if (do_step(tle, m, c)) break;
+                put_back(tle, m);
+                if (m < T && c > 0) atomicMax(&ctl->lmax[m], c);
+                tle.lidx = -1;
+            }
+            const long long t_b = tl ? clock64() : 0;
+            if (tl && t_b - t_a > 100) atomicMax((unsigned long long*)&tl[n * 8 + 2], (unsigned long long)(t_b - t_a));
             // ---- my parked pixel: events at n, then frame n+1 (what the next barrier needs) --------
             int lm_next = 0;
-            bool tail = false;
             if (cur.lidx >= 0) {
+                long long t0 = 0, t1 = 0, t2 = 0;
+                if (tl) {
+                    t0 = clock64();
+                    // touch the entry: waits for its loads
+                    asm volatile("" ::"f"(cur.b), "f"(cur.l), "f"(cur.tm), "r"(cur.xb[0]), "r"(cur.xb[1]), "r"(cur.xb[2]));
+                    t1 = clock64();
+                }
                 do_events(cur, n, fs, fg);
+                if (tl) t2 = clock64();
                 int c = 0;
-                if (n + 1 < T && !do_step(cur, n + 1, c)) tail = true;
-                else { put_back(cur, n + 1); lm_next = max(lm_next, c); }
+                const bool quiet = n + 1 < T && !do_step(cur, n + 1, c);
+                if (tl && n + 16 < V2E_MAX_FRAMES) {
+                    unsigned long long* x = (unsigned long long*)&tl[(n + 16) * 8];
+                    atomicMax(x + 0, (unsigned long long)(t1 - t0));
+                    atomicMax(x + 1, (unsigned long long)(t2 - t1));
+                    atomicMax(x + 2, (unsigned long long)(clock64() - t2));
+                }
+                if (quiet) {
+                    tle = cur;  // quiet at n+1: carried on during the next round
+                    tle_m = n + 2;
+                } else {
+                    put_back(cur, n + 1);
+                    lm_next = max(lm_next, c);
+                }
+                cur.lidx = -1;
             }
             // more parked pixels than threads (dense events, phase 1): carried to their next park here
-            for (int q = rt + nrt; q < ln; q += nrt) {
+            for (int q = slot_in_round(n) + (phase1 ? nrt : nslots2); q < ln; q += (phase1 ? nrt : nslots2)) {
                 RaEntry ex;
                 load_entry(ex, s_list[q], n);
                 do_events(ex, n, fs, fg);
@@ -833,36 +895,21 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             }
             lm_next = __reduce_max_sync(0xffffffffu, lm_next);
             if (lane == 0 && lm_next > 0 && n + 1 < T) atomicMax(&ctl->lmax[n + 1], lm_next);
-            if (tl && rt == 0) tl[n * 8 + 5] = clock64();
+            if (tl) atomicMax((unsigned long long*)&tl[n * 8 + 5], (unsigned long long)(clock64() - t_b));
             ra_fence_cta();
-            ra_named_sync(bar, nrt);  // parks at n+1 and lmax[n+1] are complete
+            ra_named_sync(bar, nrt);  // parks at n+1 (and later) and lmax[n+1] are complete
             if (rt == 0) {
                 if (n + 1 < T) arrive(n + 1);
                 if (phase1) ctl->handover = ra_lds_volatile(&ctl->stream_cnt[T - 1]) >= kRaStreamWarps;
                 if (tl) tl[n * 8 + 3] = clock64();
             }
 
-            // ---- while the barrier of frame n+1 is in flight ---------------------------------------
-            nxt.lidx = -1;
+            // ---- while the barrier of frame n+1 is in flight: list its pixels, fetch mine ------------
             if (n + 1 < T) {
                 build_list(n + 1, rt, nrt);
                 ra_named_sync(bar, nrt);
                 ln = ra_lds_volatile(&ctl->listn[(n + 1) & 1]);
-                if (rt < ln) load_entry(nxt, s_list[rt], n + 1);
-            }
-            if (tail) {  // carry the pixel of this round through n+2.. until it fires again
-                int m = n + 2, c = 0;
-                for (; m < T; ++m)
-                    if (do_step(cur, m, c)) break;
-                put_back(cur, m);
-                if (m < T && c > 0) atomicMax(&ctl->lmax[m], c);
-            }
-            if (tl && rt == 0) tl[n * 8 + 6] = clock64();
-            ra_fence_cta();  // re-parks at n+2.. are listed after the next round's first barrier
-            cur = nxt;
-            if (phase1 && n + 1 < T) {
-                ra_named_sync(1, kRaResolveThreads);  // the hand-over flag is in place
-                if (ra_lds_volatile(&ctl->handover)) {
+                if (phase1 && ra_lds_volatile(&ctl->handover)) {
                     // the stream warps are waiting at barrier 2: from round n+1 on everybody works
                     if (rt == 0) ctl->phase2 = n + 1;
                     ra_named_sync(2, kRaThreads);
@@ -870,8 +917,12 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                     nrt = kRaThreads;
                     bar = 2;
                 }
+                const int q = slot_in_round(n + 1);
+                if (q < ln) load_entry(cur, s_list[q], n + 1);
             }
+            if (tl && rt == 0) tl[n * 8 + 6] = clock64();
         }
+        if (tle.lidx >= 0) put_back(tle, T);  // (its last round was T-2: nothing left to evaluate)
         if (phase1) {  // the resolve warps finished the chain on their own
             if (rt == 0) ctl->phase2 = T;
             ra_named_sync(2, kRaThreads);

@@ -101,7 +101,8 @@ class EventEmulator(nn.Module):
             raw_capacity: Optional[int] = None,
             debug_maps: bool = False,
             debug_shot_imax: int = 24,
-            lazy_num_events: bool = False):
+            lazy_num_events: bool = False,
+            integer_frames: Optional[bool] = None):
         super().__init__()
         if output_mode not in ("raw", "voxel_grid"):
             raise ValueError("output_mode must be 'raw' or 'voxel_grid'")
@@ -163,6 +164,10 @@ class EventEmulator(nn.Module):
         self.debug_maps = debug_maps
         self.debug_shot_imax = debug_shot_imax
         self.lazy_num_events = lazy_num_events
+        # None: uint8 frames are integer by construction, float frames are not assumed to be.
+        # True: the caller guarantees integer-valued frames in 0..255 (what every reader of the
+        # reference produces); a violation is detected on the device and raised as ValueError.
+        self.integer_frames = integer_frames
         self.last_debug = {}
         self.noise_rate_array = None
         self.timestamp_mem = None
@@ -255,6 +260,7 @@ class EventEmulator(nn.Module):
         cfg.rn_neg = float(1. / self._neg_nominal_host.reshape(1))
         cfg.shot_inten_m1 = float(torch.tensor(self.SHOT_NOISE_INTEN_FACTOR - 1, dtype=f32))
         cfg.philox_rounds = self.philox_rounds
+        cfg.frames_integer = int(bool(self.integer_frames) or frame_dtype == torch.uint8)
         self._lut = lin_log_lut(self._dev)
         cfg.lut = self._lut.data_ptr()
         return cfg
@@ -270,6 +276,18 @@ class EventEmulator(nn.Module):
             self._workspace = torch.zeros(self._launch.workspace_bytes, dtype=torch.uint8,
                                           device=self._dev)
         return self._launch
+
+    @staticmethod
+    def _raise_on_status(status: int) -> None:
+        if status == _cabi.STATUS_NONINTEGER_FRAMES:
+            raise ValueError("integer_frames=True was asserted but a frame value is not an "
+                             "integer in 0..255: the outputs of this pack are invalid")
+
+    def check_status(self) -> None:
+        """Raise if the last pack reported a contract violation (synchronises)."""
+        meta = getattr(self, "_last_meta", None)
+        if meta is not None:
+            self._raise_on_status(int(meta[2].item()))
 
     @property
     def resolved_engine(self) -> Optional[str]:
@@ -329,8 +347,11 @@ class EventEmulator(nn.Module):
         pk.pos_thres = self.pos_thres.data_ptr()
         pk.neg_thres = self.neg_thres.data_ptr()
         pk.noise_rate = ops._ptr(self.noise_rate_array)
-        num_events = torch.empty(1, dtype=torch.int64, device=dev)
-        pk.num_events = num_events.data_ptr()
+        # one zeroed scratch tensor: [0:2] num_events (int64), [2] status, [4:4+T] max_iters
+        meta = torch.zeros(4 + num_frames, dtype=torch.int32, device=dev)
+        num_events = meta[0:2].view(torch.int64)
+        pk.num_events = meta.data_ptr()
+        pk.status = meta.data_ptr() + 8
         keep = [frames]
         if self.output_mode == "raw":
             cap = self.raw_capacity or 4 * P * (num_frames - 1)
@@ -354,8 +375,8 @@ class EventEmulator(nn.Module):
         pk.philox_seed = self.philox_seed
         pk.philox_offset = self._pack_counter
         self._pack_counter += 1
-        mx = torch.zeros(num_frames, dtype=torch.int32, device=dev)
-        pk.max_iters = mx.data_ptr()
+        mx = meta[4:]
+        pk.max_iters = meta.data_ptr() + 16
         dbg = {}
         if self.debug_maps:
             dbg = dict(pol=torch.zeros((num_frames - 1, P), dtype=torch.int8, device=dev),
@@ -376,11 +397,14 @@ class EventEmulator(nn.Module):
                          self.timestamp_mem, out, num_events, self._workspace)
 
         self.last_debug = dict(max_iters=mx, **dbg)
+        self._last_meta = meta
         if self.lazy_num_events and self.output_mode != "raw":
             # extension: keep the pipeline asynchronous; num_events is a 1-element device tensor
+            # (call check_status() at a convenient sync point when integer_frames=True)
             self.num_events = num_events
             return out, num_events
-        n = int(num_events.item())          # python int, like the reference (forces a sync)
+        n, status = meta[0:4].view(torch.int64).tolist()   # python int, like the reference (sync)
+        self._raise_on_status(status)
         self.num_events = n
         if self.output_mode == "raw":
             rows = out[:min(n, out.size(0))]
