@@ -48,6 +48,8 @@ EMU = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, s
            refractory_period_s=0.001, leak_rate_hz=0.1, shot_noise_rate_hz=1,
            pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)     # cfg2 params + model_v2e2v.py:56-57
 ALGO_BYTES_PER_PIXEL_PACK = 92      # 9 f32 frames + 5 f32 bins + 6 planes in + 3 planes out
+# measured DRAM bytes per launch (ncu --set full, profiles/r01_*): (workload, noise, engine)
+TRAFFIC_BYTES = {("cfg3", "philox", "persistent"): 55447040 + 3553024}
 
 
 def peaks():
@@ -77,7 +79,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
@@ -175,37 +177,46 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the public API with host frames ("e2e") ------------------------------
     copy_stream = torch.cuda.Stream(dev)
-    stage = [[torch.empty_like(packs[s][0]) for _ in range(2)] for s in range(S)]
-    ready = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
-    freed = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
     nev_host = torch.zeros(S, dtype=torch.int64).pin_memory()
-    for em in ems:
-        em.reset()
 
-    def e2e_step(kk):
-        b = kk & 1
-        for s in range(S):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[s][b])
-                stage[s][b].copy_(pinned[s][kk % ring], non_blocking=True)     # H2D, pinned
-                ready[s][b].record(copy_stream)
-        for s in range(S):
-            torch.cuda.current_stream(dev).wait_event(ready[s][b])
-            _, n = ems[s](stage[s][b], stamps(kk))
-            freed[s][b].record()
-            nev_host[s:s + 1].copy_(n, non_blocking=True)                      # D2H result
-    for kk in range(Wm):
-        e2e_step(kk)
-    barrier()
-    t0 = time.perf_counter()
-    for kk in range(Wm, Wm + K):
-        e2e_step(kk)
-    torch.cuda.synchronize(dev)
-    e2e_s = reduce_max(time.perf_counter() - t0)
-    barrier()
-    e2e_value = world * pxf_step * K / e2e_s / 1e9
+    def run_e2e(host_packs):
+        """K steps of: H2D copy of the pack from pinned host memory (double-buffered on a copy
+        stream), EventEmulator.forward, D2H read of num_events."""
+        stage = [[torch.empty_like(host_packs[s][0], device=dev) for _ in range(2)] for s in range(S)]
+        ready = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
+        freed = [[torch.cuda.Event() for _ in range(2)] for _ in range(S)]
+        for em in ems:
+            em.reset()
+
+        def step(kk):
+            b = kk & 1
+            for s in range(S):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[s][b])
+                    stage[s][b].copy_(host_packs[s][kk % ring], non_blocking=True)   # H2D, pinned
+                    ready[s][b].record(copy_stream)
+            for s in range(S):
+                torch.cuda.current_stream(dev).wait_event(ready[s][b])
+                _, n = ems[s](stage[s][b], stamps(kk))
+                freed[s][b].record()
+                nev_host[s:s + 1].copy_(n, non_blocking=True)                        # D2H result
+        for kk in range(Wm):
+            step(kk)
+        barrier()
+        t0 = time.perf_counter()
+        for kk in range(Wm, Wm + K):
+            step(kk)
+        torch.cuda.synchronize(dev)
+        secs = reduce_max(time.perf_counter() - t0)
+        barrier()
+        return world * pxf_step * K / secs / 1e9
+
+    e2e_value = run_e2e(pinned)
     h2d = S * H * W * T_FRAMES * 4
     d2h = S * 8
+    # same, with the frames as the reference's readers hold them on the host (uint8)
+    pinned_u8 = [[p.to(torch.uint8).pin_memory() for p in seqp] for seqp in pinned]
+    e2e_u8_value = run_e2e(pinned_u8)
 
     if rank != 0:
         return
@@ -228,9 +239,16 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "EventEmulator.forward on frames copied from pinned host memory each "
                         "step (double-buffered), num_events read back each step"},
+        "e2e_uint8_frames": {"value": round(e2e_u8_value, 3), "unit": "Gpixel-frames/s",
+                             "h2d_bytes_per_step": h2d // 4, "d2h_bytes_per_step": d2h,
+                             "note": "as e2e, frames passed as uint8 (what the reference's "
+                                     "readers hold before .float()); results are bit-identical"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": None,
+                     "frac": round(achieved / peak, 4), "traffic": TRAFFIC_BYTES.get(
+                         (args.workload, args.noise, ems[0].resolved_engine)),
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                       "ncu --set full capture (profiles/), bytes per launch",
                      "peak_source": peak_src, "kernel": "k_persistent" if
                      ems[0].resolved_engine == "persistent" else "k_phase_a/k_phase_b",
                      "algorithmic_bytes_per_launch": algo_bytes,
@@ -319,12 +337,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--noise", default="philox", choices=["philox", "off"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "persistent", "stepwise"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "persistent", "runahead", "stepwise"])
     ap.add_argument("--philox-rounds", type=int, default=10)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
