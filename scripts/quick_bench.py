@@ -10,7 +10,7 @@ def run(H, W, engine, noise, fdt=torch.float32, packs=30, T=10, rounds=10):
     if noise == "off":
         cfg.update(leak_rate_hz=0, shot_noise_rate_hz=0)
     torch.manual_seed(0)
-    em = EventEmulator(device="cuda", engine=engine, noise_mode=noise, philox_rounds=rounds, **cfg)
+    em = EventEmulator(device="cuda", engine=engine, noise_mode=noise, philox_rounds=rounds, integer_frames=bool(int(__import__("os").environ.get("V2E_INTF","1"))), **cfg)
     g = torch.Generator(device="cuda").manual_seed(1)
     # device-generated random-walk video, several distinct packs (inputs > L2 in total)
     nvid = 8

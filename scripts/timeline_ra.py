@@ -11,7 +11,7 @@ noise = sys.argv[3] if len(sys.argv) > 3 else "philox"
 cfg = dict(gc.CFG2)
 if noise == "off":
     cfg.update(leak_rate_hz=0, shot_noise_rate_hz=0)
-em = EventEmulator(device="cuda", engine="runahead", noise_mode=noise, lazy_num_events=True, **cfg)
+em = EventEmulator(device="cuda", engine="runahead", noise_mode=noise, lazy_num_events=True, integer_frames=bool(int(__import__("os").environ.get("V2E_INTF","1"))), **cfg)
 T = 10
 for k, fr, tfr in gc.video(1, 4, T, H, W):
     em(fr.cuda(), tfr)
@@ -32,9 +32,8 @@ stat("stream: frame1 done (from start)", fr[:, 0, 0] - t0[:, 0])
 stat("stream: per-frame period", np.diff(fr[:, :, 0], axis=1))
 stat("stream: last frame done", fr[:, -1, 0] - t0[:, 0])
 stat("resolve: wait grid barrier", fr[:, :, 4] - fr[:, :, 1])
-stat("resolve: release -> arrive", fr[:, :, 3] - fr[:, :, 4])
-stat("   slowest tail (per CTA)", fr[:, :, 2])
-stat("   slowest events+step (per CTA)", fr[:, :, 5])
+stat("resolve: tail+events+step (thread 0)", fr[:, :, 5] - fr[:, :, 4])
+stat("resolve: wait slowest + arrive", fr[:, :, 3] - fr[:, :, 5])
 stat("resolve: list+load", fr[:, :, 6] - fr[:, :, 3])
 stat("resolve: round period", np.diff(fr[:, :, 1], axis=1))
 stat("resolve: list length", fr[:, :, 7])
@@ -45,13 +44,10 @@ stat("normalise+store", tl[:, 0, 5] - tl[:, 0, 4])
 stat("total", tl[:, 0, 5] - t0[:, 0])
 for n in range(1, T):
     f = lambda k: np.median(tl[:, n, k] - t0[:, 0])
-    print(f"  round {n}: start {f(1):8.0f} released {f(4):8.0f} arrived {f(3):8.0f} listed {f(6):8.0f} | max tail {np.median(tl[:, n, 2]):6.0f} max ev {np.median(tl[:, n, 5]):6.0f} (worst CTA {tl[:, n, 2].max():6.0f} {tl[:, n, 5].max():6.0f}) | stream done {f(0):8.0f}  list {np.median(tl[:, n, 7]):5.0f}")
+    print(f"  round {n}: start {f(1):8.0f} released {f(4):8.0f} own work {f(5):8.0f} arrived {f(3):8.0f} listed {f(6):8.0f} | stream done {f(0):8.0f}  list {np.median(tl[:, n, 7]):5.0f}")
 
-for n in range(1, T):
-    x = tl[:, n + 16, :3]
-    print(f"  round {n}: slowest thread per CTA (median over CTAs / worst): entry-load wait {np.median(x[:,0]):6.0f}/{x[:,0].max():6.0f}  events {np.median(x[:,1]):6.0f}/{x[:,1].max():6.0f}  step {np.median(x[:,2]):6.0f}/{x[:,2].max():6.0f}")
-
-for n in range(1, T):
-    x = tl[:, n + 16, :]
-    k = int(np.argmax(x[:, 3]))
-    print(f"  round {n}: slowest do_events over the chip: total {x[k,3]:6.0f} = fetch+load-wait {x[k,4]:6.0f} + diff_count {x[k,5]:6.0f} + iterate/stores {x[k,6]:6.0f}; cnt*1000+fin {x[k,7]:6.0f} | median CTA: {np.median(x[:,3]):6.0f} = {np.median(x[:,4]):6.0f} + {np.median(x[:,5]):6.0f} + {np.median(x[:,6]):6.0f}")
+for r, n in ((16, 5), (20, 6)):
+    x = tl[:, r:r + 4, :].reshape(tl.shape[0], 32)
+    print(f"round {n}: per-warp critical-section cycles, median over CTAs per warp id:")
+    print("   " + " ".join(f"{np.median(x[:, w]):5.0f}" for w in range(32)))
+    print(f"   per-CTA max: median {np.median(x.max(1)):6.0f}  p95 {np.percentile(x.max(1),95):6.0f}  max {x.max():6.0f}; all warps: median {np.median(x):6.0f}")

@@ -254,8 +254,10 @@ __device__ __forceinline__ PixelA diff_count(float nw, float base, float pos, fl
     r.pol = live ? (up ? 1.f : -1.f) : 0.f;
     r.C = live ? (up ? pos : neg) : 0.f;
     const float den = fadd(r.C, 1e-9f);
-    r.cnt = 0;
-    if (__builtin_expect(live && ad >= den, 0)) r.cnt = count_div(ad, den);
+    // one code path for every lane: the quotient is always formed (the division is ~10
+    // instructions; a divergent "only on a crossing" branch costs a warp more than that)
+    const int q = (int)floorf(fdiv(ad, den));
+    r.cnt = (live && ad >= den) ? q : 0;
     return r;
 }
 
@@ -280,33 +282,6 @@ __device__ __forceinline__ FrameGlobals frame_globals(int mx, float duration, fl
 // Returns final_evts_frame for this pixel (post-refractory event count incl. shot events).
 //   pol/C/cnt: phase-A results; tm: timestamp_mem (updated in place)
 //   shot_mode: 0 none, 1 injected (reads sq.shot_rand), 2 philox candidate with uniform u
-// First iteration i in [i0, cnt) that the refractory gate accepts, i.e. with
-// fsub(ts_i, tm) > Tr where ts_i = fadd(t0, fmul(step, i+1)); cnt if there is none.  Every
-// operation is monotone non-decreasing in i, so the accepted iterations form a suffix and the
-// answer can be bracketed from an estimate instead of walking all refused iterations; the
-// predicate itself is evaluated exactly as the reference does (v2e_model.py:419,469).
-static __device__ __noinline__ int first_accept(int i0, int cnt, float t0, float step, float tm,
-                                                float Tr) {
-    auto pred = [&](int i) { return fsub(fadd(t0, fmul(step, (float)(i + 1))), tm) > Tr; };
-    if (pred(i0)) return i0;
-    if (!pred(cnt - 1)) return cnt;
-    int lo = i0, hi = cnt - 1;  // pred(lo) is false, pred(hi) is true
-    const int est = (int)__fdividef(fsub(fadd(Tr, tm), t0), step);  // ~ (i+1) at the threshold
-#pragma unroll 1
-    for (int k = est - 2; k <= est + 1; ++k) {
-        if (k <= lo) continue;
-        if (k >= hi) break;
-        if (pred(k)) { hi = k; break; }
-        lo = k;
-    }
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (pred(mid)) hi = mid;
-        else lo = mid;
-    }
-    return hi;
-}
-
 template <int R, class VoxAdd, class Emit>
 __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq, const FrameSc& fs,
                                              const FrameGlobals& g, int n, int p, float pol,
@@ -314,19 +289,31 @@ __device__ __forceinline__ int iterate_pixel(const CfgDev& cfg, const SeqDev& sq
                                              float u, VoxAdd vox_add, Emit emit) {
     int final_cnt = 0;
     if (shot_mode == 0 && g.gate) {
-        // no shot noise at this pixel and the gate is on (v2e_model.py:469): iterations [0,cnt)
-        // all carry an event, the gate refuses most of them.  Jump over the refused ones.
+        // No shot noise at this pixel and the gate is on (v2e_model.py:469): iterations [0,cnt)
+        // all carry an event and the gate refuses most of them.  Iteration j is accepted iff
+        //     fsub(fadd(t0, fmul(step, j+1)), tm) > Tr                       (:419, :469-470)
+        // and every operation is monotone non-decreasing in j, so the accepted iterations after
+        // the last accepted one form a suffix: jump to its first element from an estimate and
+        // fix it up with the exact predicate (evaluated as the reference does).  One loop trip
+        // per ACCEPTED event, the same code for every lane (no divergent variants).
+        const float t0 = fs.t_bin_prev, step = g.ts_step, Tr = sq.Tr;
+        const float rstep = __fdividef(1.0f, step);
+        auto pred = [&](int j) { return fsub(fadd(t0, fmul(step, (float)(j + 1))), tm) > Tr; };
         int i = 0;
         while (i < cnt) {
-            if (cnt - i > 3) {
-                i = first_accept(i, cnt, fs.t_bin_prev, g.ts_step, tm, sq.Tr);
-                if (i >= cnt) break;
-            }
-            const float ts = fadd(fs.t_bin_prev, fmul(g.ts_step, (float)(i + 1)));
-            ++i;
-            if (!(fsub(ts, tm) > sq.Tr)) continue;
+            // (j+1)*step + t0 - tm > Tr  <=>  j+1 > (Tr + tm - t0)/step   (estimate only)
+            int j = (int)floorf((Tr + tm - t0) * rstep) - 1;
+            j = min(max(j, i), cnt);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (j < cnt && !pred(j)) ++j;
+            while (j < cnt && !pred(j)) ++j;   // estimate too low by more than 3 (never seen)
+            while (j > i && pred(j - 1)) --j;  // estimate too high
+            if (j >= cnt) break;
+            const float ts = fadd(t0, fmul(step, (float)(j + 1)));
             tm = ts;
             final_cnt += 1;
+            i = j + 1;
             if (cfg.output_mode == V2E_OUT_RAW) {
                 emit(ts, pol);
             } else {  // v2e_model.py:478-502

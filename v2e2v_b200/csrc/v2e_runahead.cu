@@ -45,6 +45,9 @@ constexpr int kRaPPT = 8;                                          // pixels per
 constexpr int kRaGroups = kRaPPT / 4;
 constexpr int kRaTileMaxPx = kRaStreamThreads * kRaPPT;            // 6400
 constexpr int kRaWarps = kRaThreads / 32;
+// threshold / leak planes in shared memory: [slot e of a group][group], fixed stride so that the
+// slot offset is an immediate in the load instruction
+constexpr int kRaSlotStride = kRaStreamThreads * kRaGroups;  // groups per tile (capacity)
 constexpr int kRaParkDone = 0xff;  // park byte of a pixel the resolve warps carried to the end
 static_assert(V2E_MAX_FRAMES < kRaParkDone, "park byte holds the frame index");
 
@@ -239,10 +242,9 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     FrameSc* s_fr = (FrameSc*)(smem_raw + kRaFrOff);
     RaCtl* ctl = (RaCtl*)(smem_raw + kRaCtlOff);
     float* s_vox = (float*)(smem_raw + kRaHeaderBytes);                  // [nb][tpa]
-    float* s_pos = s_vox + (size_t)nb * tpa;                             // [tpa]
-    float* s_neg = s_pos + tpa;                                          // [tpa]
-    float* s_lkn = s_neg + tpa;                                          // [tpa] if leak
-    unsigned char* s_park = (unsigned char*)(s_lkn + (leak ? tpa : 0));  // [tpa]
+    float2* s_pn = (float2*)(s_vox + (size_t)nb * tpa);                  // [4][kRaSlotStride] {pos, neg}
+    float* s_lkn = (float*)(s_pn + 4 * kRaSlotStride);                   // [4][kRaSlotStride] if leak
+    unsigned char* s_park = (unsigned char*)(s_lkn + (leak ? 4 * kRaSlotStride : 0));  // [tpa]
     unsigned short* s_list = (unsigned short*)(s_park + tpa);            // [tpa]
     const unsigned a_lut = ra_smem_u32(s_lut);
     const size_t felem = FDT == V2E_DT_U8 ? 1 : (FDT == V2E_DT_BF16 ? 2 : 4);
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     const float shot_m1 = cfg.shot_inten_m1;
 
     // index of a tile-local pixel in the [slot][group] planes
-    auto slot_of = [&](int lidx) { return (lidx & 3) * prm.tile_groups + (lidx >> 2); };
+    auto slot_of = [&](int lidx) { return (lidx & 3) * kRaSlotStride + (lidx >> 2); };
     // (L, I) of frame m for the pixel of entry e: from the bytes fetched with the entry, or
     // (arbitrary float frames, packs of more than 13 frames) from global memory
     auto fetch_li = [&](const RaEntry& e, int m, float& L, float& I) {
@@ -366,13 +368,9 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     // frame n: the events of a parked pixel (v2e_model.py:449-522)
     auto do_events = [&](RaEntry& e, int n, const FrameSc& fs, const FrameGlobals& fg) {
         const int p = tile_px0 + e.lidx;
-        const long long c0 = tl ? clock64() : 0;
         float L, I;
         fetch_li(e, n, L, I);
-        long long c1 = 0, c2 = 0;
-        if (tl) { asm volatile("" ::"f"(L), "f"(e.b), "f"(e.l), "f"(e.tm)); c1 = clock64(); }
-        const PixelA a = diff_count(cutoff ? e.l : L, e.b, s_pos[slot_of(e.lidx)], s_neg[slot_of(e.lidx)]);
-        if (tl) { asm volatile("" ::"f"(a.C), "r"(a.cnt)); c2 = clock64(); }
+        const PixelA a = diff_count(cutoff ? e.l : L, e.b, s_pn[slot_of(e.lidx)].x, s_pn[slot_of(e.lidx)].y);
         int mode = 0;
         float u = 0.f;
         if (shot && a.pol != 0.f && fg.mx > 0) {
@@ -396,26 +394,17 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             nev += fin;
             if (GENERIC && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
         }
-        if (tl && n + 16 < V2E_MAX_FRAMES) {
-            const long long c3 = clock64();
-            unsigned long long* x = (unsigned long long*)&tl[(n + 16) * 8];
-            const unsigned long long tot = (unsigned long long)(c3 - c0);
-            if (atomicMax(x + 3, tot) < tot) {
-                x[4] = c1 - c0; x[5] = c2 - c1; x[6] = c3 - c2; x[7] = a.cnt * 1000 + fin;
-            }
-        }
     };
     // frame m without events: low-pass, leak, diff.  Returns true if the pixel fires (or is a
     // shot candidate) at m; cnt = its event count.
     auto do_step = [&](RaEntry& e, int m, int& cnt) -> bool {
         const int p = tile_px0 + e.lidx;
-        const FrameSc fm = s_fr[m];
-        const float ps = s_pos[slot_of(e.lidx)], ng = s_neg[slot_of(e.lidx)];
+        const float2 pn = s_pn[slot_of(e.lidx)];
         float L, I;
         fetch_li(e, m, L, I);
         float nw = L;
         if (cutoff) {
-            e.l = lowpass(e.l, L, I, e.small ? fm.s_small : fm.s_large);
+            e.l = lowpass(e.l, L, I, e.small ? s_fr[m].s_small : s_fr[m].s_large);
             nw = e.l;
         }
         unsigned shot_bytes = 0;
@@ -432,27 +421,35 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             } else if (leak) {
                 z = __ldg(sq.leak_randn + (size_t)(m - 1) * P + p);
             }
-            if (leak) e.b = leak_sub(e.b, s_lkn[slot_of(e.lidx)], jit, z, fm.sdt, ps);
+            if (leak) e.b = leak_sub(e.b, s_lkn[slot_of(e.lidx)], jit, z, s_fr[m].sdt, pn.x);
         }
-        const PixelA a = diff_count(nw, e.b, ps, ng);
+        // diff / polarity / threshold as diff_count(); the count (a division) only if it fires
+        const float diff = fsub(nw, e.b);
+        const float ad = fabsf(diff);
+        const bool live = ad > 1e-6f;
+        const bool up = diff > 0.f;
+        const float C = live ? (up ? pn.x : pn.y) : 0.f;
+        const float den = fadd(C, 1e-9f);
+        const bool cross = live && ad >= den;
         bool cand = false;
-        if (shot && a.pol != 0.f) {
+        if (shot && live) {
             if (philox) {
                 const unsigned byte = (shot_bytes >> (8 * (p & 3))) & 0xffu;
-                const float thr256 = shot_thr256(a.pol > 0.f ? fm.kp : fm.kn, shot_m1, I, a.C);
+                const float thr256 = shot_thr256(up ? s_fr[m].kp : s_fr[m].kn, shot_m1, I, C);
                 float uu;
                 cand = ra_shot_candidate<R>(sq.philox_ctr, m, p, byte, thr256, uu);
             } else {
                 cand = true;
             }
         }
+        cnt = 0;
+        if (cross) cnt = (int)floorf(fdiv(ad, den));
         if (GENERIC) {
-            if (sq.dbg_pol) sq.dbg_pol[(size_t)(m - 1) * P + p] = (signed char)a.pol;
-            if (sq.dbg_cnt) sq.dbg_cnt[(size_t)(m - 1) * P + p] = a.cnt;
+            if (sq.dbg_pol) sq.dbg_pol[(size_t)(m - 1) * P + p] = live ? (up ? 1 : -1) : 0;
+            if (sq.dbg_cnt) sq.dbg_cnt[(size_t)(m - 1) * P + p] = cnt;
             if (sq.dbg_final) sq.dbg_final[(size_t)(m - 1) * P + p] = 0;
         }
-        cnt = a.cnt;
-        return a.cnt > 0 || cand;
+        return cross || cand;
     };
     // hand the pixel back: state -> planes; park byte = frame m it fires at next, or "done"
     auto put_back = [&](const RaEntry& e, int m) {
@@ -469,8 +466,10 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         ra_st_relaxed(&slots[n * kRaMaxTiles + tile], (unsigned)ra_lds_volatile(&ctl->lmax[n]) + 1u);
     };
     auto build_list = [&](int n, int rt, int nrt) {
-        // every park byte of frame n written by the stream warps must be visible first
-        while (ra_lds_volatile(&ctl->stream_cnt[n]) < kRaStreamWarps) {}
+        // every park byte of frame n written by the stream warps must be visible first.  Thread 0
+        // has waited for that in arrive(n); the others only get here early in phase 1, where a
+        // spinning resolve warp would steal issue slots from the stream warps: back off.
+        while (ra_lds_volatile(&ctl->stream_cnt[n]) < kRaStreamWarps) __nanosleep(200);
         ra_fence_cta();
         const unsigned pat = (unsigned)n * 0x01010101u;
         const int chunks = tpa >> 4;
@@ -529,16 +528,14 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 // update the entries of the pixels that fire
                 *(float4*)(sq.tmem + p0) = t4;
                 // the constant planes stay in shared memory for both roles
-                // layout [slot e][group]: scalar accesses of a warp are conflict-free
+                // layout [slot e][group]: the accesses of a warp are conflict-free
                 {
-                    const int tg = prm.tile_groups;
                     const float* pp = &ld_pos[g].x; const float* np_ = &ld_neg[g].x;
                     const float* rp = &ld_nra[g].x;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        s_pos[e * tg + gl] = pp[e];
-                        s_neg[e * tg + gl] = np_[e];
-                        if (leak) s_lkn[e * tg + gl] = fmul(cfg.leak_rate, rp[e]);
+                        s_pn[e * kRaSlotStride + gl] = make_float2(pp[e], np_[e]);
+                        if (leak) s_lkn[e * kRaSlotStride + gl] = fmul(cfg.leak_rate, rp[e]);
                     }
                 }
                 const int y = p0 / cfg.W, x = p0 - y * cfg.W;
@@ -561,24 +558,27 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
 
         // shared-window addresses kept opaque so that they stay in registers (the compiler
         // otherwise rebuilds the generic->shared conversion at every use)
-        unsigned a_lut_r = a_lut, a_pos = ra_smem_u32(s_pos), a_park = ra_smem_u32(s_park);
-        asm volatile("" : "+r"(a_lut_r), "+r"(a_pos), "+r"(a_park));
-        const unsigned d_neg = (unsigned)tpa * 4u, d_lkn = (unsigned)tpa * 8u;  // plane strides
-        const unsigned d_slot = (unsigned)prm.tile_groups * 4u;                 // slot stride
-        float* const g_base = sq.base + tile_px0;
-        float* const g_lp = sq.lp + tile_px0;
-        unsigned dead = 0;  // bit j: pixel j is parked (its state belongs to the resolve warps)
+        unsigned a_lut_r = a_lut, a_pn = ra_smem_u32(s_pn), a_lk = ra_smem_u32(s_lkn),
+                 a_park = ra_smem_u32(s_park);
+        asm volatile("" : "+r"(a_lut_r), "+r"(a_pn), "+r"(a_lk), "+r"(a_park));
+        unsigned dead = 0;     // bit j: pixel j is parked (its state belongs to the resolve warps)
+        unsigned err_hi = 0;   // INTF: OR of (x + 1.5*2^23) ^ 0x4B400000: bits >= 8 set <=> out of 0..255
+        unsigned err_lo = 0;   // INTF: OR of (rounded x) ^ x: non-zero <=> not an integer
         bool nonint = false;
+        // running frame pointers of my groups (next frame = + P elements)
+        const unsigned char* fptr[kRaGroups];
         RaVec<FDT> xcur[kRaGroups];
+        const size_t fstride = (size_t)P * felem;
 #pragma unroll
         for (int g = 0; g < kRaGroups; ++g) {
+            const int gl = g * kRaStreamThreads + ts;
+            fptr[g] = (const unsigned char*)sq.frames + ((size_t)P + tile_px0 + gl * 4) * felem;
             xcur[g] = RaVec<FDT>{};
-            if (valid[g] && T > 1)
-                xcur[g] = ra_load4<FDT>(sq.frames, (long long)P + tile_px0 +
-                                                       (g * kRaStreamThreads + ts) * 4);
+            if (valid[g] && T > 1) xcur[g] = ra_load4<FDT>(fptr[g], 0);
         }
         for (int n = 1; n < T; ++n) {
-            const FrameSc fs = s_fr[n];
+            const float s_small = s_fr[n].s_small, s_large = s_fr[n].s_large;
+            const float sdt = s_fr[n].sdt, kp = s_fr[n].kp, kn = s_fr[n].kn;
             int lm_frame = 0;  // max event count among the pixels this thread parks at frame n
 #pragma unroll
             for (int g = 0; g < kRaGroups; ++g) {
@@ -586,11 +586,9 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 const int gl = g * kRaStreamThreads + ts;
                 float z[4] = {0.f, 0.f, 0.f, 0.f};
                 unsigned shot_bytes = 0;
-                // thresholds / leak rate of pixel e of this group: plane[e][gl] in shared memory
-                const unsigned a_px = a_pos + (unsigned)gl * 4u;
-                auto ld_pos = [&](int e) { return ra_lds_f1(a_px + (unsigned)e * d_slot); };
-                auto ld_neg = [&](int e) { return ra_lds_f1(a_px + d_neg + (unsigned)e * d_slot); };
-                auto ld_lkn = [&](int e) { return ra_lds_f1(a_px + d_lkn + (unsigned)e * d_slot); };
+                // thresholds {pos, neg} / leak rate of pixel e of this group: plane[e][gl]
+                const unsigned a_g = a_pn + (unsigned)gl * 8u;
+                const unsigned a_gl = a_lk + (unsigned)gl * 4u;
                 if (philox) {
                     const uint4 w = noise_words<R>(sq.philox_ctr, n, (unsigned)(g0 + gl), 0);
                     shot_bytes = w.z;
@@ -615,13 +613,23 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int e = 2 * h + q;
-                        bool ok;
-                        float xv;
-                        const int v = ra_elem<FDT>(xcur[g], e, ok, xv) & 0xff;
-                        li[q] = ra_lds_f2(a_lut_r + 8u * (unsigned)v);
-                        if (FDT != V2E_DT_U8 && __builtin_expect(!ok, 0)) {
-                            if (INTF) nonint = true;  // contract violation: reported, not served
-                            else li[q] = log_inten_slow(xv);  // fp64 lin_log, emulator_utils.py:13-37
+                        if constexpr (FDT == V2E_DT_U8) {
+                            li[q] = ra_lds_f2(a_lut_r + 8u * ((xcur[g].v >> (8 * e)) & 0xffu));
+                        } else {
+                            float xv;
+                            bool okdummy;
+                            (void)ra_elem<FDT>(xcur[g], e, okdummy, xv);
+                            const float y = __fadd_rn(xv, 12582912.0f);
+                            const unsigned yb = __float_as_uint(y);
+                            li[q] = ra_lds_f2(a_lut_r + 8u * (yb & 0xffu));
+                            if (INTF) {
+                                err_hi |= yb ^ 0x4B400000u;
+                                err_lo |= __float_as_uint(__fsub_rn(y, 12582912.0f)) ^ __float_as_uint(xv);
+                            } else if (__builtin_expect(
+                                           (yb & 0xffffff00u) != 0x4B400000u ||
+                                               __fsub_rn(y, 12582912.0f) != xv, 0)) {
+                                li[q] = log_inten_slow(xv);  // fp64 lin_log, emulator_utils.py:13-37
+                            }
                         }
                     }
 #pragma unroll
@@ -632,27 +640,25 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                         Lk[e] = L;
                         float nw = L;
                         if (cutoff) {
-                            const float s = (small_mask >> j) & 1u ? fs.s_small : fs.s_large;
+                            const float s = (small_mask >> j) & 1u ? s_small : s_large;
                             lpv[j] = lowpass(lpv[j], L, I, s);
                             nw = lpv[j];
                         }
-                        float pe = 0.f;
-                        if (leak) {
-                            pe = ld_pos(e);
-                            base[j] = leak_sub(base[j], ld_lkn(e), jit, z[e], fs.sdt, pe);
-                        }
+                        const float2 pn = ra_lds_f2(a_g + (unsigned)(e * kRaSlotStride * 8));
+                        if (leak)
+                            base[j] = leak_sub(base[j], ra_lds_f1(a_gl + (unsigned)(e * kRaSlotStride * 4)),
+                                               jit, z[e], sdt, pn.x);
                         // diff / polarity / threshold (v2e_model.py:375,394-404), see diff_count()
                         const float diff = fsub(nw, base[j]);
                         const float ad = fabsf(diff);
                         const bool live = ad > 1e-6f;
                         const bool up = diff > 0.f;
-                        const float C = up ? (leak ? pe : ld_pos(e)) : ld_neg(e);
+                        const float C = up ? pn.x : pn.y;
                         bool maybe = live && ad >= fadd(C, 1e-9f);
                         if (shot) {
                             if (philox) {
                                 // first stage of the candidate test (0 threshold if !live)
-                                const float thr256 =
-                                    shot_thr256(up ? fs.kp : fs.kn, shot_m1, I, live ? C : 0.f);
+                                const float thr256 = shot_thr256(up ? kp : kn, shot_m1, I, live ? C : 0.f);
                                 maybe = maybe ||
                                         ra_byte_to_float((shot_bytes >> (8 * e)) & 0xffu) < thr256;
                             } else {
@@ -672,11 +678,12 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 const RaVec<FDT> xprev = xcur[g];  // (dead unless a shot candidate needs I again)
                 // this group's pixels of the next frame: in flight while the other group and the
                 // next frame's first group are computed
-                if (n + 1 < T)
-                    xcur[g] = ra_load4<FDT>(sq.frames, (long long)(n + 1) * P + tile_px0 + gl * 4);
+                fptr[g] += fstride;
+                if (n + 1 < T) xcur[g] = ra_load4<FDT>(fptr[g], 0);
                 if (flag) {
                     // rare per thread (~3 % of pixel-frames): exact count, second stage of the shot
                     // test, park.  Everything is recomputed from the registers of the pixel.
+                    const unsigned poff = (unsigned)(gl * 4) * 4u;  // byte offset in the tile's planes
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (!((flag >> e) & 1u)) continue;
@@ -685,7 +692,8 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                         const float diff = fsub(nw, base[j]);
                         const float ad = fabsf(diff);
                         const bool up = diff > 0.f;
-                        const float C = up ? ld_pos(e) : ld_neg(e);
+                        const float2 pn = ra_lds_f2(a_g + (unsigned)(e * kRaSlotStride * 8));
+                        const float C = up ? pn.x : pn.y;
                         const float den = fadd(C, 1e-9f);
                         // floor(ad/den) == 1 <=> den <= ad < 2*den (same argument as diff_count)
                         int cnt = 0;
@@ -699,7 +707,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                                 const int v = ra_elem<FDT>(xprev, e, ok, xv) & 0xff;
                                 const float I = ok ? ra_lds_f2(a_lut_r + 8u * (unsigned)v).y
                                                    : log_inten_slow(xv).y;
-                                const float thr256 = shot_thr256(up ? fs.kp : fs.kn, shot_m1, I, C);
+                                const float thr256 = shot_thr256(up ? kp : kn, shot_m1, I, C);
                                 float u;
                                 cand = ra_shot_candidate<R>(sq.philox_ctr, n, tile_px0 + gl * 4 + e,
                                                             (shot_bytes >> (8 * e)) & 0xffu, thr256, u);
@@ -710,8 +718,8 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                         if (cnt > 0 || cand) {
                             // state as of frame n (before its events) -> state planes; ordered
                             // before the stream_cnt[n] increment by the fence below
-                            ra_stg_strong(g_base + gl * 4 + e, base[j]);
-                            if (cutoff) ra_stg_strong(g_lp + gl * 4 + e, lpv[j]);
+                            ra_stg_strong((float*)((char*)(sq.base + tile_px0) + poff) + e, base[j]);
+                            if (cutoff) ra_stg_strong((float*)((char*)(sq.lp + tile_px0) + poff) + e, lpv[j]);
                             if (GENERIC && sq.dbg_cnt)
                                 sq.dbg_cnt[(size_t)(n - 1) * P + tile_px0 + gl * 4 + e] = cnt;
                             asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_park + (unsigned)(gl * 4 + e)),
@@ -731,6 +739,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 if (tl) atomicMax((unsigned long long*)&tl[n * 8 + 0], (unsigned long long)clock64());
             }
         }
+        if (INTF && ((err_hi & 0xffffff00u) != 0u || err_lo != 0u)) nonint = true;
 
         if (INTF && nonint) ctl->nonint = 1;
         // ---- write back the state of the pixels that never left the streaming registers ---------
@@ -780,13 +789,12 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         // use disjoint quarters of the threads, so that the thread that carries a pixel of round
         // n on through n+2.. (the "tail") is not the one that serves a pixel of round n+1.
         auto slot_in_round = [&](int n) {
-            if (phase1) return rt;
-            // warps of one parity serve the parked pixels of even rounds, the others those of odd
-            // rounds: list slot = (index of my warp among its parity) * 32 + lane
-            const int w = rt >> 5;
-            return ((w ^ n) & 1) ? (1 << 20) : (((w >> 1) << 5) | (rt & 31));
+            // phase 2: consecutive rounds use disjoint blocks of 8 warps (256 list slots), so
+            // that the warps carrying last round's quiet pixels on are not the ones serving
+            // this round's parked pixels
+            return phase1 ? rt : (rt + kRaThreads - (256 * n) % kRaThreads) % kRaThreads;
         };
-        const int nslots2 = ((kRaThreads / 32 + 1) / 2) * 32;  // list slots served per round in phase 2
+        const int nslots2 = kRaThreads;
         RaEntry cur, tle;   // my pixel of this round; my pixel of the last round still to carry on
         int tle_m = 0;      // ... from this frame on
         cur.lidx = tle.lidx = -1;
@@ -837,11 +845,11 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             ra_named_sync(bar, nrt);
             const FrameGlobals fg = frame_globals(ra_lds_volatile(&ctl->mx), sq.duration, sq.Tr);
             const FrameSc fs = s_fr[n];
+            const long long t_sec = tl ? clock64() : 0;
 
             // ---- the pixel I still carry from the last round: on through its frames until it fires
             //      again (re-park) or the pack ends.  Its park byte must be in place before the
             //      list of frame n+1 is built, i.e. before the barrier below. ------------------------
-            const long long t_a = tl ? clock64() : 0;
             if (tle.lidx >= 0) {
                 int m = tle_m, c = 0;
                 for (; m < T; ++m)
@@ -850,28 +858,12 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 if (m < T && c > 0) atomicMax(&ctl->lmax[m], c);
                 tle.lidx = -1;
             }
-            const long long t_b = tl ? clock64() : 0;
-            if (tl && t_b - t_a > 100) atomicMax((unsigned long long*)&tl[n * 8 + 2], (unsigned long long)(t_b - t_a));
             // ---- my parked pixel: events at n, then frame n+1 (what the next barrier needs) --------
             int lm_next = 0;
             if (cur.lidx >= 0) {
-                long long t0 = 0, t1 = 0, t2 = 0;
-                if (tl) {
-                    t0 = clock64();
-                    // touch the entry: waits for its loads
-                    asm volatile("" ::"f"(cur.b), "f"(cur.l), "f"(cur.tm), "r"(cur.xb[0]), "r"(cur.xb[1]), "r"(cur.xb[2]));
-                    t1 = clock64();
-                }
                 do_events(cur, n, fs, fg);
-                if (tl) t2 = clock64();
                 int c = 0;
                 const bool quiet = n + 1 < T && !do_step(cur, n + 1, c);
-                if (tl && n + 16 < V2E_MAX_FRAMES) {
-                    unsigned long long* x = (unsigned long long*)&tl[(n + 16) * 8];
-                    atomicMax(x + 0, (unsigned long long)(t1 - t0));
-                    atomicMax(x + 1, (unsigned long long)(t2 - t1));
-                    atomicMax(x + 2, (unsigned long long)(clock64() - t2));
-                }
                 if (quiet) {
                     tle = cur;  // quiet at n+1: carried on during the next round
                     tle_m = n + 2;
@@ -895,7 +887,9 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             }
             lm_next = __reduce_max_sync(0xffffffffu, lm_next);
             if (lane == 0 && lm_next > 0 && n + 1 < T) atomicMax(&ctl->lmax[n + 1], lm_next);
-            if (tl) atomicMax((unsigned long long*)&tl[n * 8 + 5], (unsigned long long)(clock64() - t_b));
+            if (tl && rt == 0) tl[n * 8 + 5] = clock64();
+            if (tl && lane == 0 && (n == 5 || n == 6))   // per-warp time of the critical section
+                tl[(16 + (n - 5) * 4) * 8 + warp] = clock64() - t_sec;
             ra_fence_cta();
             ra_named_sync(bar, nrt);  // parks at n+1 (and later) and lmax[n+1] are complete
             if (rt == 0) {
@@ -973,9 +967,14 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         double a = 0., b = 0., c = 0., d = 0.;
         for (int i = tid; i < tiles; i += 32) {
             unsigned long long v[4];
+            bool all;
+            do {  // the four loads are in flight together
+                all = true;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                do { v[k] = ra_ld_relaxed64(&wk.ra_stat[4 * i + k]); } while (v[k] == 0ull);
+                for (int k = 0; k < 4; ++k) v[k] = ra_ld_relaxed64(&wk.ra_stat[4 * i + k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) all = all && v[k] != 0ull;
+            } while (!all);
             a += __longlong_as_double((long long)~v[0]);
             b += __longlong_as_double((long long)~v[1]);
             c += __longlong_as_double((long long)~v[2]);
@@ -1086,7 +1085,8 @@ static RaPlan ra_make_plan(const CfgDev& cfg, int n_seq, int T) {
     const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
     const size_t tpa = (size_t)tg * 4;
     // header + voxel planes + threshold planes (+ leak plane) + park bytes + park list
-    const size_t smem = kRaHeaderBytes + tpa * 4 * cfg.nb + tpa * 8 + (leak ? tpa * 4 : 0) + tpa + tpa * 2;
+    const size_t smem = kRaHeaderBytes + tpa * 4 * cfg.nb + (size_t)kRaSlotStride * 4 * 8 +
+                        (leak ? (size_t)kRaSlotStride * 4 * 4 : 0) + tpa + tpa * 2;
     if (smem > (size_t)g_ra_smem_optin) return pl;
     (void)T;
     pl.ok = 1;
