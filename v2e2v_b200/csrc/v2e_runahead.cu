@@ -76,6 +76,7 @@ struct RaParams {
     int n_seq;
     int tiles_per_seq;
     int tile_groups;  // 4-pixel groups per tile
+    int use_bytes;    // the frame values of the whole pack are kept as bytes in shared memory
     SeqWork* work;
     long long* timeline;  // development aid (V2E_TIMELINE=1): [cta][frame][8] clock64 stamps
     SeqDev seq[V2E_MAX_SEQ_PER_LAUNCH];
@@ -109,8 +110,17 @@ __device__ __forceinline__ float ra_ldg_strong(const float* p) {
     asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ float4 ra_ldg_strong4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void ra_stg_strong(float* p, float v) {
     asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void ra_red_add(float* p, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ int ra_lds_volatile(const int* p) {
     int v;
@@ -196,13 +206,10 @@ __device__ __forceinline__ bool ra_shot_candidate(unsigned long long ctr, int n,
 }
 
 // a parked pixel in the registers of a resolve thread
-constexpr int kRaXbWords = 3;  // frame values of frames 1..12 as bytes
 struct RaEntry {
-    int lidx;      // tile-local pixel index; < 0: empty
-    bool small;    // a (ps, qs) pixel: even row and even column
-    bool bytes_ok; // xb holds the frame values (integer-valued 0..255) of frames >= the park frame
+    int lidx;    // tile-local pixel index; < 0: empty
+    bool small;  // a (ps, qs) pixel: even row and even column
     float b, l, tm;
-    unsigned xb[kRaXbWords];
 };
 
 // NOISE: 0 = no noise, 1 = PHILOX leak + shot (the V2E2VNet wiring), 2 = generic: every feature
@@ -241,11 +248,15 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     float2* s_lut = (float2*)(smem_raw + kRaLutOff);
     FrameSc* s_fr = (FrameSc*)(smem_raw + kRaFrOff);
     RaCtl* ctl = (RaCtl*)(smem_raw + kRaCtlOff);
-    float* s_vox = (float*)(smem_raw + kRaHeaderBytes);                  // [nb][tpa]
-    float2* s_pn = (float2*)(s_vox + (size_t)nb * tpa);                  // [4][kRaSlotStride] {pos, neg}
+    float2* s_pn = (float2*)(smem_raw + kRaHeaderBytes);                 // [4][kRaSlotStride] {pos, neg}
     float* s_lkn = (float*)(s_pn + 4 * kRaSlotStride);                   // [4][kRaSlotStride] if leak
-    unsigned char* s_park = (unsigned char*)(s_lkn + (leak ? 4 * kRaSlotStride : 0));  // [tpa]
+    float* s_base = s_lkn + (leak ? 4 * kRaSlotStride : 0);              // [tpa] state of parked pixels
+    float* s_lp = s_base + tpa;                                          // [tpa] if cutoff
+    unsigned char* s_park = (unsigned char*)(s_lp + (cutoff ? tpa : 0)); // [tpa]
     unsigned short* s_list = (unsigned short*)(s_park + tpa);            // [tpa]
+    unsigned char* s_byte = (unsigned char*)(s_list + tpa);              // [T-1][tpa] if use_bytes
+    const bool use_bytes = prm.use_bytes != 0;
+    float* const g_vox = (float*)sq.voxel;  // un-normalised accumulators live in the output grid
     const unsigned a_lut = ra_smem_u32(s_lut);
     const size_t felem = FDT == V2E_DT_U8 ? 1 : (FDT == V2E_DT_BF16 ? 2 : 4);
 
@@ -300,9 +311,6 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     for (int i = tid; i < T; i += kRaThreads) s_fr[i] = prm.fr[seq][i];
     for (int i = tid; i < (int)(sizeof(RaCtl) / 4); i += kRaThreads) ((int*)ctl)[i] = 0;
     {
-        float4* v4 = (float4*)s_vox;
-        const int n4 = nb * tpa / 4;
-        for (int i = tid; i < n4; i += kRaThreads) v4[i] = make_float4(0, 0, 0, 0);
         uint4* p4 = (uint4*)s_park;
         for (int i = tid; i < tpa / 16; i += kRaThreads) p4[i] = make_uint4(0, 0, 0, 0);
     }
@@ -319,13 +327,21 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
 
     // index of a tile-local pixel in the [slot][group] planes
     auto slot_of = [&](int lidx) { return (lidx & 3) * kRaSlotStride + (lidx >> 2); };
-    // (L, I) of frame m for the pixel of entry e: from the bytes fetched with the entry, or
-    // (arbitrary float frames, packs of more than 13 frames) from global memory
+    // (L, I) of frame m for a parked pixel: from the byte the stream warps left in shared memory
+    // when they passed frame m, or (frame not streamed yet / arbitrary float frames / no room
+    // for the byte planes) from global memory
+    int streamed = 0;  // frames whose bytes are known to be complete
+    bool bytes_ok = use_bytes;
     auto fetch_li = [&](const RaEntry& e, int m, float& L, float& I) {
-        const int k = m - 1;
-        if (e.bytes_ok && k < 4 * kRaXbWords) {
-            const unsigned w = k < 4 ? e.xb[0] : (k < 8 ? e.xb[1] : e.xb[2]);
-            const unsigned v = (w >> (8 * (k & 3))) & 0xffu;
+        if (bytes_ok && m > streamed) {
+            if (ra_lds_volatile(&ctl->stream_cnt[m]) >= kRaStreamWarps) {
+                ra_fence_cta();
+                streamed = m;
+            }
+            if (ra_lds_volatile(&ctl->nonint)) bytes_ok = false;
+        }
+        if (bytes_ok && m <= streamed) {
+            const unsigned v = s_byte[(size_t)(m - 1) * tpa + e.lidx];
             const float2 li = ra_lds_f2(a_lut + 8u * v);
             L = li.x;
             I = li.y;
@@ -333,37 +349,18 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             log_inten(s_lut, load_frame1<FDT>(sq.frames, (long long)m * P + tile_px0 + e.lidx), L, I);
         }
     };
-    // state of a pixel parked at frame n: strong loads (written by a stream thread or another
-    // resolve thread of this CTA) and the pixel's values in frames n.. , all issued together.
-    // Runs while the grid barrier is in flight, so the latency is off the critical path.
+    // state of a pixel parked at frame n: base / lp from shared memory (left there by the stream
+    // thread that parked it, or by the resolve thread that carried it on), timestamp_mem from its
+    // plane (a strong load, issued while the grid barrier is in flight)
     auto load_entry = [&](RaEntry& e, int lidx, int n) {
+        (void)n;
         e.lidx = lidx;
         const int p = tile_px0 + lidx;
-        e.b = ra_ldg_strong(sq.base + p);
-        e.l = cutoff ? ra_ldg_strong(sq.lp + p) : 0.f;
         e.tm = ra_ldg_strong(sq.tmem + p);
-        float xv[4 * kRaXbWords];
-#pragma unroll
-        for (int k = 0; k < 4 * kRaXbWords; ++k) {
-            const int m = k + 1;
-            xv[k] = (m >= n && m < T) ? load_frame1<FDT>(sq.frames, (long long)m * P + p) : 0.f;
-        }
+        e.b = s_base[lidx];
+        e.l = cutoff ? s_lp[lidx] : 0.f;
         const int yy = p / cfg.W, xx = p - yy * cfg.W;
         e.small = ((yy | xx) & 1) == 0;
-        bool ok_all = true;
-#pragma unroll
-        for (int w = 0; w < kRaXbWords; ++w) {
-            unsigned word = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                bool ok;
-                const int v = ra_index(xv[4 * w + k], ok);
-                ok_all = ok_all && ok;
-                word |= (unsigned)(v & 0xff) << (8 * k);
-            }
-            e.xb[w] = word;
-        }
-        e.bytes_ok = ok_all;
     };
     // frame n: the events of a parked pixel (v2e_model.py:449-522)
     auto do_events = [&](RaEntry& e, int n, const FrameSc& fs, const FrameGlobals& fg) {
@@ -383,10 +380,13 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 mode = 1;
             }
         }
-        float* vp = s_vox + e.lidx;
+        // voxel accumulation: straight into the output grid (L2), in the reference's order per
+        // address (one thread at a time owns a pixel; same-address atomics of a thread are
+        // performed in program order)
+        float* vp = g_vox + p;
         const int fin = iterate_pixel<R>(
             cfg, sq, fs, fg, n, p, a.pol, a.C, a.cnt, I, e.tm, mode, u,
-            [&](int bin, float val) { vp[bin * tpa] = fadd(vp[bin * tpa], val); },
+            [&](int bin, float val) { ra_red_add(vp + (size_t)bin * P, val); },
             [&](float, float) {});
         if (fin > 0) {
             ra_stg_strong(sq.tmem + p, e.tm);
@@ -451,11 +451,10 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         }
         return cross || cand;
     };
-    // hand the pixel back: state -> planes; park byte = frame m it fires at next, or "done"
+    // hand the pixel back: state -> shared memory; park byte = frame m it fires at next, or "done"
     auto put_back = [&](const RaEntry& e, int m) {
-        const int p = tile_px0 + e.lidx;
-        ra_stg_strong(sq.base + p, e.b);
-        if (cutoff) ra_stg_strong(sq.lp + p, e.l);
+        s_base[e.lidx] = e.b;
+        if (cutoff) s_lp[e.lidx] = e.l;
         s_park[e.lidx] = (unsigned char)(m < T ? m : kRaParkDone);
     };
     // the tile's parks at frame n are final: tell the other tiles its max (no flag, no fence:
@@ -527,6 +526,9 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 // timestamp_mem lives in its state plane for the whole pack: the resolve warps
                 // update the entries of the pixels that fire
                 *(float4*)(sq.tmem + p0) = t4;
+                // the output grid doubles as the accumulator: zero it before any event can land
+                for (int b = 0; b < nb; ++b)
+                    *(float4*)(g_vox + (size_t)b * P + p0) = make_float4(0, 0, 0, 0);
                 // the constant planes stay in shared memory for both roles
                 // layout [slot e][group]: the accesses of a warp are conflict-free
                 {
@@ -559,8 +561,8 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         // shared-window addresses kept opaque so that they stay in registers (the compiler
         // otherwise rebuilds the generic->shared conversion at every use)
         unsigned a_lut_r = a_lut, a_pn = ra_smem_u32(s_pn), a_lk = ra_smem_u32(s_lkn),
-                 a_park = ra_smem_u32(s_park);
-        asm volatile("" : "+r"(a_lut_r), "+r"(a_pn), "+r"(a_lk), "+r"(a_park));
+                 a_park = ra_smem_u32(s_park), a_byte = ra_smem_u32(s_byte);
+        asm volatile("" : "+r"(a_lut_r), "+r"(a_pn), "+r"(a_lk), "+r"(a_park), "+r"(a_byte));
         unsigned dead = 0;     // bit j: pixel j is parked (its state belongs to the resolve warps)
         unsigned err_hi = 0;   // INTF: OR of (x + 1.5*2^23) ^ 0x4B400000: bits >= 8 set <=> out of 0..255
         unsigned err_lo = 0;   // INTF: OR of (rounded x) ^ x: non-zero <=> not an integer
@@ -605,6 +607,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                     z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
                 }
                 unsigned flag = 0;  // bit e: pixel e may have to be parked at this frame
+                unsigned bytes4 = 0;  // the four frame values as bytes (for the resolve warps)
                 float Lk[4];        // lin-log value of the four pixels (the rare path needs it)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -615,6 +618,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                         const int e = 2 * h + q;
                         if constexpr (FDT == V2E_DT_U8) {
                             li[q] = ra_lds_f2(a_lut_r + 8u * ((xcur[g].v >> (8 * e)) & 0xffu));
+                            bytes4 = xcur[g].v;
                         } else {
                             float xv;
                             bool okdummy;
@@ -622,6 +626,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                             const float y = __fadd_rn(xv, 12582912.0f);
                             const unsigned yb = __float_as_uint(y);
                             li[q] = ra_lds_f2(a_lut_r + 8u * (yb & 0xffu));
+                            bytes4 |= (yb & 0xffu) << (8 * e);
                             if (INTF) {
                                 err_hi |= yb ^ 0x4B400000u;
                                 err_lo |= __float_as_uint(__fsub_rn(y, 12582912.0f)) ^ __float_as_uint(xv);
@@ -629,6 +634,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                                            (yb & 0xffffff00u) != 0x4B400000u ||
                                                __fsub_rn(y, 12582912.0f) != xv, 0)) {
                                 li[q] = log_inten_slow(xv);  // fp64 lin_log, emulator_utils.py:13-37
+                                nonint = true;               // (its byte is meaningless)
                             }
                         }
                     }
@@ -675,6 +681,9 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                     }
                 }
                 flag &= ~(dead >> (g * 4));
+                if (use_bytes)
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_byte + (unsigned)((n - 1) * tpa + gl * 4)),
+                                 "r"(bytes4) : "memory");
                 const RaVec<FDT> xprev = xcur[g];  // (dead unless a shot candidate needs I again)
                 // this group's pixels of the next frame: in flight while the other group and the
                 // next frame's first group are computed
@@ -683,7 +692,6 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 if (flag) {
                     // rare per thread (~3 % of pixel-frames): exact count, second stage of the shot
                     // test, park.  Everything is recomputed from the registers of the pixel.
-                    const unsigned poff = (unsigned)(gl * 4) * 4u;  // byte offset in the tile's planes
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (!((flag >> e) & 1u)) continue;
@@ -716,10 +724,10 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                             }
                         }
                         if (cnt > 0 || cand) {
-                            // state as of frame n (before its events) -> state planes; ordered
+                            // state as of frame n (before its events) -> shared memory; ordered
                             // before the stream_cnt[n] increment by the fence below
-                            ra_stg_strong((float*)((char*)(sq.base + tile_px0) + poff) + e, base[j]);
-                            if (cutoff) ra_stg_strong((float*)((char*)(sq.lp + tile_px0) + poff) + e, lpv[j]);
+                            s_base[gl * 4 + e] = base[j];
+                            if (cutoff) s_lp[gl * 4 + e] = lpv[j];
                             if (GENERIC && sq.dbg_cnt)
                                 sq.dbg_cnt[(size_t)(n - 1) * P + tile_px0 + gl * 4 + e] = cnt;
                             asm volatile("st.shared.u8 [%0], %1;" ::"r"(a_park + (unsigned)(gl * 4 + e)),
@@ -730,7 +738,8 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                     }
                 }
             }
-            // this warp has streamed frame n: publish park bytes, parked state and max
+            if (!INTF && nonint) ctl->nonint = 1;  // before the release below
+            // this warp has streamed frame n: publish frame bytes, park bytes, parked state and max
             lm_frame = __reduce_max_sync(0xffffffffu, lm_frame);
             if (lane == 0) {
                 if (lm_frame > 0) atomicMax(&ctl->lmax[n], lm_frame);
@@ -927,19 +936,41 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
     __syncthreads();
     if (tl && tid == 0) tl[3] = clock64();
 
+    // ---- the pixels the chain owned: final base / lp from shared memory to their planes ---------
+    for (int c = tid; c < (tpa >> 2); c += kRaThreads) {
+        const unsigned w = *(const unsigned*)(s_park + c * 4);
+        if (w == 0u) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (((w >> (8 * e)) & 0xffu) == 0u) continue;
+            const int lidx = c * 4 + e;
+            sq.base[tile_px0 + lidx] = s_base[lidx];
+            if (cutoff) sq.lp[tile_px0 + lidx] = s_lp[lidx];
+        }
+    }
+
     // ---- statistics of the un-normalised grid (utils/event_process.py:166-174) ---------------------
-    const bool voxel_out = cfg.output_mode != V2E_OUT_RAW;
+    // The accumulators sit in the output grid (L2): every red of this CTA was issued before the
+    // barrier above and is ordered by the fences of the chain; read them back with strong loads.
+    const bool normalise = cfg.output_mode == V2E_OUT_VOXEL;
+    const int nchunks = nb * ngroups;  // float4 chunks of this tile's part of the grid
+    auto chunk_ptr = [&](int i) {
+        const int b = i / ngroups, gl = i - b * ngroups;
+        return g_vox + (size_t)b * P + tile_px0 + gl * 4;
+    };
     double s1 = 0., s2 = 0., nz = 0.;
-    if (cfg.output_mode == V2E_OUT_VOXEL) {
-        for (int b = 0; b < nb; ++b)
-            for (int i = tid; i < tile_px; i += kRaThreads) {
-                const float v = s_vox[b * tpa + i];
-                if (v != 0.f) {
-                    s1 += (double)v;
-                    s2 += (double)v * (double)v;
+    if (normalise) {
+        for (int i = tid; i < nchunks; i += kRaThreads) {
+            const float4 v4 = ra_ldg_strong4(chunk_ptr(i));
+            const float* vp = &v4.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (vp[e] != 0.f) {
+                    s1 += (double)vp[e];
+                    s2 += (double)vp[e] * (double)vp[e];
                     nz += 1.;
                 }
-            }
+        }
     }
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_down_sync(0xffffffffu, s1, o);
@@ -988,7 +1019,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         }
         if (tid == 0) {
             float mean = 0.f, den = 1.f, on = 0.f;
-            if (c > 0. && cfg.output_mode == V2E_OUT_VOXEL) {
+            if (c > 0. && normalise) {
                 mean = fdiv((float)a, (float)c);
                 den = fadd(sqrtf(fsub(fdiv((float)b, (float)c), fmul(mean, mean))), 1e-8f);
                 on = 1.f;
@@ -996,34 +1027,23 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             if (tl) tl[4] = clock64();
             ctl->stat[0] = mean; ctl->stat[1] = den; ctl->stat[2] = on;
             if (tile == 0) *sq.num_events = (unsigned long long)d;
-            if (sq.status && ctl->nonint) *sq.status = V2E_STATUS_NONINTEGER_FRAMES;
+            if (INTF && sq.status && ctl->nonint) *sq.status = V2E_STATUS_NONINTEGER_FRAMES;
         }
     }
     __syncthreads();
 
-    // ---- normalise and store the voxel tile (utils/event_process.py:175) ----------------------------
-    if (voxel_out) {
+    // ---- normalise in place (utils/event_process.py:175): only chunks that hold events change ----
+    if (ctl->stat[2] != 0.f) {
         const float mean = ctl->stat[0], den = ctl->stat[1];
-        const bool norm = ctl->stat[2] != 0.f;
-        for (int b = 0; b < nb; ++b) {
-            for (int gl = tid; gl < ngroups; gl += kRaThreads) {
-                float4 v = *(const float4*)(s_vox + b * tpa + gl * 4);
-                if (norm) {
-                    float* vp = &v.x;
+        for (int i = tid; i < nchunks; i += kRaThreads) {
+            float* ptr = chunk_ptr(i);
+            float4 v = ra_ldg_strong4(ptr);
+            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            float* vp = &v.x;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (vp[e] != 0.f) vp[e] = fdiv(fsub(vp[e], mean), den);
-                }
-                const size_t o = (size_t)b * P + tile_px0 + gl * 4;
-                if (cfg.voxel_bf16) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                    uint2 pk;
-                    pk.x = *(unsigned*)&lo; pk.y = *(unsigned*)&hi;
-                    *(uint2*)((__nv_bfloat16*)sq.voxel + o) = pk;
-                } else {
-                    __stcs((float4*)((float*)sq.voxel + o), v);
-                }
-            }
+            for (int e = 0; e < 4; ++e)
+                if (vp[e] != 0.f) vp[e] = fdiv(fsub(vp[e], mean), den);
+            __stcs((float4*)ptr, v);
         }
     }
 
@@ -1045,7 +1065,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
 // ---- host side -----------------------------------------------------------------------------------
 struct RaPlan {
     int ok;
-    int tiles_per_seq, tile_groups;
+    int tiles_per_seq, tile_groups, use_bytes;
     size_t smem;
 };
 
@@ -1084,14 +1104,22 @@ static RaPlan ra_make_plan(const CfgDev& cfg, int n_seq, int T) {
     tiles = (total_groups + tg - 1) / tg;
     const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
     const size_t tpa = (size_t)tg * 4;
-    // header + voxel planes + threshold planes (+ leak plane) + park bytes + park list
-    const size_t smem = kRaHeaderBytes + tpa * 4 * cfg.nb + (size_t)kRaSlotStride * 4 * 8 +
-                        (leak ? (size_t)kRaSlotStride * 4 * 4 : 0) + tpa + tpa * 2;
-    if (smem > (size_t)g_ra_smem_optin) return pl;
-    (void)T;
+    if (cfg.voxel_bf16) return pl;  // the f32 output grid doubles as the accumulator
+    // header + threshold planes (+ leak plane) + parked base (+ lp) + park bytes + park list
+    const size_t fixed = kRaHeaderBytes + (size_t)kRaSlotStride * 4 * 8 +
+                         (leak ? (size_t)kRaSlotStride * 4 * 4 : 0) + tpa * 4 * (cfg.cutoff_on ? 2 : 1) +
+                         tpa + tpa * 2;
+    if (fixed > (size_t)g_ra_smem_optin) return pl;
+    size_t smem = fixed;
+    int use_bytes = 0;
+    if (T > 1 && fixed + tpa * (size_t)(T - 1) <= (size_t)g_ra_smem_optin) {
+        use_bytes = 1;  // one byte per pixel and frame for the resolve warps
+        smem = fixed + tpa * (size_t)(T - 1);
+    }
     pl.ok = 1;
     pl.tiles_per_seq = tiles;
     pl.tile_groups = tg;
+    pl.use_bytes = use_bytes;
     pl.smem = smem;
     return pl;
 }
@@ -1133,6 +1161,7 @@ static int run_runahead_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     prm.n_seq = n_seq;
     prm.tiles_per_seq = pl.tiles_per_seq;
     prm.tile_groups = pl.tile_groups;
+    prm.use_bytes = pl.use_bytes;
     prm.work = (SeqWork*)workspace;
     static const bool want_timeline = getenv("V2E_TIMELINE") != nullptr;
     // the stepwise engine's accumulator area of the workspace is unused here: borrow it
