@@ -39,6 +39,10 @@ stat("resolve: round period", np.diff(fr[:, :, 1], axis=1))
 stat("resolve: list length", fr[:, :, 7])
 stat("roles done (from start)", tl[:, 0, 2] - t0[:, 0])
 stat("sync after roles", tl[:, 0, 3] - tl[:, 0, 2])
+stat("  parked state write-back", tl[:, 31, 0] - tl[:, 0, 3])
+stat("  statistics pass over the grid", tl[:, 31, 1] - tl[:, 31, 0])
+stat("  CTA reduce + publish", tl[:, 31, 2] - tl[:, 31, 1])
+stat("  wait other tiles + combine", tl[:, 0, 4] - tl[:, 31, 2])
 stat("stats barrier", tl[:, 0, 4] - tl[:, 0, 3])
 stat("normalise+store", tl[:, 0, 5] - tl[:, 0, 4])
 stat("total", tl[:, 0, 5] - t0[:, 0])

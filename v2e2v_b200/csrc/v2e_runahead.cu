@@ -362,19 +362,44 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         const int yy = p / cfg.W, xx = p - yy * cfg.W;
         e.small = ((yy | xx) & 1) == 0;
     };
+    // What the events of a parked pixel at frame n need and what does NOT depend on the image-wide
+    // max: computed while the grid barrier is in flight.
+    struct RaPrep {
+        PixelA a;    // polarity, threshold, count at frame n (v2e_model.py:375-404)
+        float I;     // rescaled intensity at frame n (shot noise)
+        float nw1;   // filtered value at frame n+1 (low-pass already advanced)
+        float I1;    // rescaled intensity at frame n+1
+    };
+    // input side of frame m: low-pass (state advanced), returns the filtered value and I
+    auto prep_step = [&](RaEntry& e, int m, float& nw, float& I) {
+        float L;
+        fetch_li(e, m, L, I);
+        nw = L;
+        if (cutoff) {
+            e.l = lowpass(e.l, L, I, e.small ? s_fr[m].s_small : s_fr[m].s_large);
+            nw = e.l;
+        }
+    };
+    auto prep_entry = [&](RaEntry& e, int n, RaPrep& pr) {
+        float L;
+        fetch_li(e, n, L, pr.I);
+        const float2 pn = s_pn[slot_of(e.lidx)];
+        pr.a = diff_count(cutoff ? e.l : L, e.b, pn.x, pn.y);
+        pr.nw1 = 0.f;
+        pr.I1 = 0.f;
+        if (n + 1 < T) prep_step(e, n + 1, pr.nw1, pr.I1);
+    };
     // frame n: the events of a parked pixel (v2e_model.py:449-522)
-    auto do_events = [&](RaEntry& e, int n, const FrameSc& fs, const FrameGlobals& fg) {
+    auto run_events = [&](RaEntry& e, int n, const RaPrep& pr, const FrameSc& fs, const FrameGlobals& fg) {
         const int p = tile_px0 + e.lidx;
-        float L, I;
-        fetch_li(e, n, L, I);
-        const PixelA a = diff_count(cutoff ? e.l : L, e.b, s_pn[slot_of(e.lidx)].x, s_pn[slot_of(e.lidx)].y);
+        const PixelA a = pr.a;
         int mode = 0;
         float u = 0.f;
         if (shot && a.pol != 0.f && fg.mx > 0) {
             if (philox) {
                 const uint4 w = noise_words<R>(sq.philox_ctr, n, (unsigned)(p >> 2), 0);
                 const unsigned byte = (w.z >> (8 * (p & 3))) & 0xffu;
-                const float thr256 = shot_thr256(a.pol > 0.f ? fs.kp : fs.kn, shot_m1, I, a.C);
+                const float thr256 = shot_thr256(a.pol > 0.f ? fs.kp : fs.kn, shot_m1, pr.I, a.C);
                 if (ra_shot_candidate<R>(sq.philox_ctr, n, p, byte, thr256, u)) mode = 2;
             } else {
                 mode = 1;
@@ -385,7 +410,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         // performed in program order)
         float* vp = g_vox + p;
         const int fin = iterate_pixel<R>(
-            cfg, sq, fs, fg, n, p, a.pol, a.C, a.cnt, I, e.tm, mode, u,
+            cfg, sq, fs, fg, n, p, a.pol, a.C, a.cnt, pr.I, e.tm, mode, u,
             [&](int bin, float val) { ra_red_add(vp + (size_t)bin * P, val); },
             [&](float, float) {});
         if (fin > 0) {
@@ -395,18 +420,11 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             if (GENERIC && sq.dbg_final) sq.dbg_final[(size_t)(n - 1) * P + p] = fin;
         }
     };
-    // frame m without events: low-pass, leak, diff.  Returns true if the pixel fires (or is a
+    // state side of frame m (no events yet): leak, diff.  Returns true if the pixel fires (or is a
     // shot candidate) at m; cnt = its event count.
-    auto do_step = [&](RaEntry& e, int m, int& cnt) -> bool {
+    auto finish_step = [&](RaEntry& e, int m, float nw, float I, int& cnt) -> bool {
         const int p = tile_px0 + e.lidx;
         const float2 pn = s_pn[slot_of(e.lidx)];
-        float L, I;
-        fetch_li(e, m, L, I);
-        float nw = L;
-        if (cutoff) {
-            e.l = lowpass(e.l, L, I, e.small ? s_fr[m].s_small : s_fr[m].s_large);
-            nw = e.l;
-        }
         unsigned shot_bytes = 0;
         if (leak || (shot && philox)) {
             float z = 0.f;
@@ -450,6 +468,11 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             if (sq.dbg_final) sq.dbg_final[(size_t)(m - 1) * P + p] = 0;
         }
         return cross || cand;
+    };
+    auto do_step = [&](RaEntry& e, int m, int& cnt) -> bool {
+        float nw, I;
+        prep_step(e, m, nw, I);
+        return finish_step(e, m, nw, I, cnt);
     };
     // hand the pixel back: state -> shared memory; park byte = frame m it fires at next, or "done"
     auto put_back = [&](const RaEntry& e, int m) {
@@ -805,6 +828,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         };
         const int nslots2 = kRaThreads;
         RaEntry cur, tle;   // my pixel of this round; my pixel of the last round still to carry on
+        RaPrep prep;        // what was computed for `cur` ahead of the barrier release
         int tle_m = 0;      // ... from this frame on
         cur.lidx = tle.lidx = -1;
         if (is_stream) {
@@ -817,14 +841,14 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             if (n_first < T) {
                 ln = ra_lds_volatile(&ctl->listn[n_first & 1]);
                 const int q = slot_in_round(n_first);
-                if (q < ln) load_entry(cur, s_list[q], n_first);
+                if (q < ln) { load_entry(cur, s_list[q], n_first); prep_entry(cur, n_first, prep); }
             }
         } else if (T > 1) {
             if (rt == 0) arrive(1);
             build_list(1, rt, nrt);
             ra_named_sync(1, kRaResolveThreads);
             ln = ra_lds_volatile(&ctl->listn[1]);
-            if (rt < ln) load_entry(cur, s_list[rt], 1);
+            if (rt < ln) { load_entry(cur, s_list[rt], 1); prep_entry(cur, 1, prep); }
         }
         const bool poller = warp == kRaStreamWarps;  // first resolve warp talks to the other tiles
         for (int n = n_first; n < T; ++n) {
@@ -856,23 +880,12 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             const FrameSc fs = s_fr[n];
             const long long t_sec = tl ? clock64() : 0;
 
-            // ---- the pixel I still carry from the last round: on through its frames until it fires
-            //      again (re-park) or the pack ends.  Its park byte must be in place before the
-            //      list of frame n+1 is built, i.e. before the barrier below. ------------------------
-            if (tle.lidx >= 0) {
-                int m = tle_m, c = 0;
-                for (; m < T; ++m)
-                    if (do_step(tle, m, c)) break;
-                put_back(tle, m);
-                if (m < T && c > 0) atomicMax(&ctl->lmax[m], c);
-                tle.lidx = -1;
-            }
             // ---- my parked pixel: events at n, then frame n+1 (what the next barrier needs) --------
             int lm_next = 0;
             if (cur.lidx >= 0) {
-                do_events(cur, n, fs, fg);
+                run_events(cur, n, prep, fs, fg);
                 int c = 0;
-                const bool quiet = n + 1 < T && !do_step(cur, n + 1, c);
+                const bool quiet = n + 1 < T && !finish_step(cur, n + 1, prep.nw1, prep.I1, c);
                 if (quiet) {
                     tle = cur;  // quiet at n+1: carried on during the next round
                     tle_m = n + 2;
@@ -885,9 +898,13 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             // more parked pixels than threads (dense events, phase 1): carried to their next park here
             for (int q = slot_in_round(n) + (phase1 ? nrt : nslots2); q < ln; q += (phase1 ? nrt : nslots2)) {
                 RaEntry ex;
+                RaPrep px;
                 load_entry(ex, s_list[q], n);
-                do_events(ex, n, fs, fg);
+                prep_entry(ex, n, px);
+                run_events(ex, n, px, fs, fg);
                 int m = n + 1, c = 0;
+                if (m < T && !finish_step(ex, m, px.nw1, px.I1, c)) ++m;
+                else if (m < T) { put_back(ex, m); lm_next = max(lm_next, c); continue; }
                 for (; m < T; ++m)
                     if (do_step(ex, m, c)) break;
                 put_back(ex, m);
@@ -921,11 +938,23 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                     bar = 2;
                 }
                 const int q = slot_in_round(n + 1);
-                if (q < ln) load_entry(cur, s_list[q], n + 1);
+                if (q < ln) { load_entry(cur, s_list[q], n + 1); prep_entry(cur, n + 1, prep); }
+            }
+            // ---- also in the shadow of that barrier: the pixel of this round that stayed quiet at
+            //      n+1 is carried on through n+2.. until it fires again (re-park) or the pack ends.
+            //      (Its park byte is in place before the list of frame n+2 is built: that happens
+            //      after the next round's second barrier.)  In phase 2 the threads that serve round
+            //      n+1 are other warps than these. ------------------------------------------------
+            if (tle.lidx >= 0) {
+                int m = tle_m, c = 0;
+                for (; m < T; ++m)
+                    if (do_step(tle, m, c)) break;
+                put_back(tle, m);
+                if (m < T && c > 0) atomicMax(&ctl->lmax[m], c);
+                tle.lidx = -1;
             }
             if (tl && rt == 0) tl[n * 8 + 6] = clock64();
         }
-        if (tle.lidx >= 0) put_back(tle, T);  // (its last round was T-2: nothing left to evaluate)
         if (phase1) {  // the resolve warps finished the chain on their own
             if (rt == 0) ctl->phase2 = T;
             ra_named_sync(2, kRaThreads);
@@ -949,6 +978,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
         }
     }
 
+    if (tl && tid == 0) tl[31 * 8 + 0] = clock64();
     // ---- statistics of the un-normalised grid (utils/event_process.py:166-174) ---------------------
     // The accumulators sit in the output grid (L2): every red of this CTA was issued before the
     // barrier above and is ordered by the fences of the chain; read them back with strong loads.
@@ -972,6 +1002,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
                 }
         }
     }
+    if (tl && tid == 0) tl[31 * 8 + 1] = clock64();
     for (int o = 16; o > 0; o >>= 1) {
         s1 += __shfl_down_sync(0xffffffffu, s1, o);
         s2 += __shfl_down_sync(0xffffffffu, s2, o);
@@ -993,6 +1024,7 @@ __global__ void __launch_bounds__(kRaThreads, 1) k_runahead(const __grid_constan
             for (int i = 0; i < kRaWarps; ++i) a += ctl->dred[i * 4 + tid];
             ra_st_relaxed64(&wk.ra_stat[4 * tile + tid], ~(unsigned long long)__double_as_longlong(a));
         }
+        if (tl && tid == 0) tl[31 * 8 + 2] = clock64();
         // fixed assignment tile -> lane and a fixed shuffle tree: deterministic, and identical in
         // every CTA of the sequence
         double a = 0., b = 0., c = 0., d = 0.;
