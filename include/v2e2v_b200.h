@@ -58,6 +58,8 @@ extern "C" {
 #define V2E_STATUS_OK 0
 #define V2E_STATUS_NONINTEGER_FRAMES 1 /* frames_integer was asserted but a value was not 0..255
                                           integer: the outputs of this pack are invalid          */
+#define V2E_STATUS_NOT_CONVERGED 2     /* fixed-point engine: internal error (the chain of per-
+                                          frame maxima did not settle): outputs are invalid      */
 
 /* noise_mode */
 #define V2E_NOISE_OFF 0       /* leak_rate_hz == 0 and shot_noise_rate_hz == 0                   */
@@ -80,6 +82,8 @@ extern "C" {
 #define V2E_ENGINE_PERSISTENT 2 /* one cooperative launch per pack, state on chip, lock-step     */
 #define V2E_ENGINE_RUNAHEAD 3   /* one cooperative launch per pack, streaming decoupled from the
                                    per-frame max: only the pixels that fire wait for it          */
+#define V2E_ENGINE_FIXPOINT 4   /* one cooperative launch per pack, the per-frame maxima are
+                                   guessed and verified: pixels never wait for each other        */
 
 /* Per-emulator static configuration (v2e/v2e_model.py:36-153). */
 typedef struct v2e_config {
@@ -205,7 +209,9 @@ int v2e_host_pack_scalars(const v2e_host_params* hp, const double* t_frames,
  * Emulate one pack for each of n_seq independent sequences (1 <= n_seq <= 16 per call).
  * Replaces EventEmulator.forward (v2e/v2e_model.py:290-536) for B=1 per sequence.  State planes
  * are updated in place; `voxel` / `raw_events` / `num_events` are written.  `workspace` must be
- * v2e_workspace_bytes() bytes, zero-initialised once by the caller, and is left zeroed. */
+ * v2e_workspace_bytes() bytes, zero-initialised once by the caller; its synchronisation words
+ * are left zeroed (the fixed-point engine keeps a hint for the next pack in it: reuse the same
+ * workspace for consecutive packs of a sequence, any content of the hint is correct). */
 int v2e_pack_forward(const v2e_config* cfg, const v2e_pack* packs, int n_seq,
                      void* workspace, size_t workspace_bytes, void* stream);
 

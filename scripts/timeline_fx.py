@@ -1,0 +1,33 @@
+"""Dump the per-CTA timeline of the fixed-point kernel (V2E_TIMELINE=1): development aid."""
+import os, sys
+os.environ["V2E_TIMELINE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tests import gpu_common as gc
+from v2e2v_b200 import EventEmulator
+
+H, W = int(sys.argv[1]), int(sys.argv[2])
+noise = sys.argv[3] if len(sys.argv) > 3 else "philox"
+cfg = dict(gc.CFG2)
+if noise == "off":
+    cfg.update(leak_rate_hz=0, shot_noise_rate_hz=0)
+em = EventEmulator(device="cuda", engine="fixpoint", noise_mode=noise, lazy_num_events=True, **cfg)
+T = 10
+for k, fr, tfr in gc.video(1, 5, T, H, W):
+    em(fr.cuda(), tfr)
+    torch.cuda.synchronize()
+    ws = em._workspace
+    tl = ws[ws.numel() - 160 * 32 * 8:].view(torch.int64).cpu().numpy().reshape(160, 32)
+    tl = tl[tl[:, 0] > 0]
+    t0 = tl[:, 0].min()
+    npass = int(tl[0, 30])
+    us = lambda a: (a - t0) / 1e3
+    print(f"pack {k}: CTAs {tl.shape[0]} passes {npass}  entries/tile mean {tl[:,28].mean():.0f} max {tl[:,28].max()} "
+          f"spill mean {tl[:,29].mean():.1f} max {tl[:,29].max()}")
+    rows = [("start", 0), ("setup done", 1), ("pass1 done", 2)]
+    for ps in range(min(npass, 8)):
+        rows += [(f"resolve{ps} done", 3 + 3 * ps), (f"barrier{ps} done", 4 + 3 * ps)]
+    rows += [("loop exit", 27), ("commit done", 31)]
+    for name, i in rows:
+        x = us(tl[:, i])
+        print(f"   {name:16s} min {x.min():8.1f}  mean {x.mean():8.1f}  max {x.max():8.1f} us")

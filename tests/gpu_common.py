@@ -7,7 +7,10 @@ import torch
 from oracle.oracle import OracleEmulator
 from tests.refharness import noise_arrays, synth_walk_pack, stamps
 
-ENGINES = ("stepwise", "persistent", "runahead")
+ENGINES = ("stepwise", "persistent", "runahead", "fixpoint")
+# engines that share the (4-pixel group, frame) Philox stage-0 stream; the fixed-point engine
+# indexes its stream by pixel (v2e_fixpoint.cu, noise_px)
+LOCKSTEP_ENGINES = ("stepwise", "persistent", "runahead")
 
 SD = dict(pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)
 CFG2 = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, sigma_thres=0.03,

@@ -27,8 +27,8 @@ def _to_cuda_frames(frames_u8, dtype=torch.float32):
 def test_golden_reference_outputs(name, engine):
     """CUDA path vs outputs of the unmodified reference (tests/golden)."""
     g = GoldenCase(name)
-    if g.raw and engine == "runahead":
-        pytest.skip("the run-ahead engine serves the voxel modes only (raw -> persistent/stepwise)")
+    if g.raw and engine in ("runahead", "fixpoint"):
+        pytest.skip("this engine serves the voxel modes only (raw -> persistent/stepwise)")
     em = gc.cuda_emulator(g.emu, engine)
     pos, neg, nra = g.planes()
     shp = (g.H, g.W)
@@ -117,11 +117,12 @@ def test_philox_mode_is_consistent_with_oracle(engine, rounds):
 
 
 def test_engines_agree_philox():
-    """Same seed/offset => all engines draw identical noise."""
+    """Same seed/offset => the lock-step engines draw identical noise; the fixed-point engine
+    (its own per-pixel stream) is compared with itself: run-to-run bit-identical."""
     cfg, H, W, T = gc.CFG2, 64, 96, 10
     pos, neg, nra = gc.make_planes(13, H, W, cfg)
     outs = []
-    for engine in gc.ENGINES:
+    for engine in gc.LOCKSTEP_ENGINES + ("fixpoint", "fixpoint"):
         torch.manual_seed(0)
         em = gc.cuda_emulator(cfg, engine, noise_mode="philox")
         em.philox_seed = 1234
@@ -131,11 +132,16 @@ def test_engines_agree_philox():
             ev, nev = em(fr.to("cuda"), tfr)
             res.append((ev.cpu().numpy(), nev, em.base_log_frame.cpu().numpy().copy()))
         outs.append(res)
-    for other in outs[1:]:
+    nl = len(gc.LOCKSTEP_ENGINES)
+    for other in outs[1:nl]:
         for a, b in zip(outs[0], other):
             assert a[1] == b[1]
             np.testing.assert_array_equal(a[2], b[2])
             np.testing.assert_allclose(a[0], b[0], rtol=VOX_RTOL, atol=VOX_ATOL)
+    for a, b in zip(outs[nl], outs[nl + 1]):
+        assert a[1] == b[1]
+        np.testing.assert_array_equal(a[2], b[2])
+        np.testing.assert_array_equal(a[0], b[0])     # integer statistics: order-free
 
 
 def test_shot_noise_rate_statistics():

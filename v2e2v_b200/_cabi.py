@@ -23,11 +23,11 @@ ERR_CUDA = -4
 ERR_WORKSPACE = -5
 ERR_NO_DEVICE = -6
 
-STATUS_OK, STATUS_NONINTEGER_FRAMES = 0, 1
+STATUS_OK, STATUS_NONINTEGER_FRAMES, STATUS_NOT_CONVERGED = 0, 1, 2
 NOISE_OFF, NOISE_INJECTED, NOISE_PHILOX = 0, 1, 2
 DT_F32, DT_U8, DT_BF16 = 0, 1, 2
 OUT_VOXEL, OUT_RAW, OUT_VOXEL_UNNORM = 0, 1, 2
-ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_PERSISTENT, ENGINE_RUNAHEAD = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_STEPWISE, ENGINE_PERSISTENT, ENGINE_RUNAHEAD, ENGINE_FIXPOINT = 0, 1, 2, 3, 4
 
 
 class Config(C.Structure):

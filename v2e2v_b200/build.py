@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libv2e2v_b200.so")
 BUILD = os.path.join(PKG, "_build")
 
-CU_SOURCES = ["v2e_api.cu", "v2e_stepwise.cu", "v2e_persistent.cu", "v2e_runahead.cu",
+CU_SOURCES = ["v2e_api.cu", "v2e_stepwise.cu", "v2e_persistent.cu", "v2e_runahead.cu", "v2e_fixpoint.cu",
               "v2e_voxel.cu"]
 C_SOURCES = ["host_scalars.c"]
 HEADERS = ["v2e_device.cuh", "v2e_engine.cuh", os.path.join("..", "..", "include", "v2e2v_b200.h")]

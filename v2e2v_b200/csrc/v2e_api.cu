@@ -112,7 +112,12 @@ int v2e_resolve_engine(const v2e_config* c, int n_seq) {
     if (rc != V2E_OK) return rc;
     if (n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH) return V2E_ERR_BAD_ARG;
     if (c->engine == V2E_ENGINE_STEPWISE) return V2E_ENGINE_STEPWISE;
-    if (c->engine < V2E_ENGINE_AUTO || c->engine > V2E_ENGINE_RUNAHEAD) return V2E_ERR_BAD_ARG;
+    if (c->engine < V2E_ENGINE_AUTO || c->engine > V2E_ENGINE_FIXPOINT) return V2E_ERR_BAD_ARG;
+    if (c->engine == V2E_ENGINE_FIXPOINT) {
+        const int fx = fixpoint_fits(cfg, c->frame_dtype, n_seq);
+        if (fx < 0) return fx;
+        return fx ? V2E_ENGINE_FIXPOINT : V2E_ERR_UNSUPPORTED;
+    }
     if (c->engine == V2E_ENGINE_RUNAHEAD) {
         const int ra = runahead_fits(cfg, c->frame_dtype, n_seq);
         if (ra < 0) return ra;
@@ -146,6 +151,8 @@ int v2e_pack_forward(const v2e_config* c, const v2e_pack* packs, int n_seq, void
     const int engine = v2e_resolve_engine(c, n_seq);
     if (engine < 0) return engine;
     cudaStream_t st = (cudaStream_t)stream;
+    if (engine == V2E_ENGINE_FIXPOINT)
+        return run_fixpoint(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
     if (engine == V2E_ENGINE_RUNAHEAD)
         return run_runahead(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
     if (engine == V2E_ENGINE_PERSISTENT)

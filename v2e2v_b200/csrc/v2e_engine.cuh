@@ -9,6 +9,7 @@
 namespace v2e {
 
 constexpr int kMaxPartials = 2048;
+constexpr size_t kTimelineBytes = 160 * 32 * 8;  // development aid: [cta][32] clock stamps
 constexpr int kRaMaxTiles = 160;  // run-ahead engine: tiles (CTAs) per sequence, <= SM count
 
 // Per-sequence work area inside the caller's workspace.  Zero on entry, zero on exit.
@@ -28,8 +29,19 @@ struct SeqWork {
 };
 using StepWork = SeqWork;
 
+// Per-sequence work area of the fixed-point engine.  `slot` is zero on entry and on exit;
+// `guess` is a hint that survives from pack to pack (any content is correct, see v2e_fixpoint.cu).
+struct FxWork {
+    // grid barrier records, double-buffered by pass parity: per tile 16 words of per-frame maxima
+    // (two u16 each), 10 words of statistics partials, word 31 = pass tag (0: not arrived)
+    unsigned slot[2][kRaMaxTiles][32];
+    unsigned exit_count;
+    unsigned pad[3];
+    unsigned guess[V2E_MAX_FRAMES];  // last pack's per-frame max event count + 1 (0: none yet)
+};
+
 struct StepLayout {
-    size_t work_off, vox_off, cntpol_off, total;
+    size_t work_off, vox_off, cntpol_off, fx_off, fxstate_off, tl_off, total;
     int n_partials;
 };
 
@@ -39,7 +51,10 @@ inline StepLayout step_layout(const CfgDev& cfg, int n_seq) {
     l.work_off = 0;
     l.vox_off = up(sizeof(SeqWork) * (size_t)n_seq);
     l.cntpol_off = up(l.vox_off + (size_t)n_seq * cfg.nb * cfg.P * sizeof(float));
-    l.total = up(l.cntpol_off + (size_t)n_seq * cfg.P * sizeof(int));
+    l.fx_off = up(l.cntpol_off + (size_t)n_seq * cfg.P * sizeof(int));
+    l.fxstate_off = up(l.fx_off + sizeof(FxWork) * (size_t)n_seq);
+    l.tl_off = up(l.fxstate_off + (size_t)n_seq * 3 * cfg.P * sizeof(float));
+    l.total = up(l.tl_off + kTimelineBytes);
     const size_t N = (size_t)cfg.nb * cfg.P;
     size_t np = (N + 256 * 16 - 1) / (256 * 16);
     if (np < 1) np = 1;
@@ -114,5 +129,8 @@ int run_runahead(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack*
 // 1 if the persistent / run-ahead engine can hold n_seq sequences of this config on chip
 int persistent_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
 int runahead_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
+int run_fixpoint(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs, int n_seq,
+                 void* workspace, cudaStream_t st);
+int fixpoint_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
 
 }  // namespace v2e

@@ -94,7 +94,7 @@ class EventEmulator(nn.Module):
             device="cuda",
             # ---- extensions (keyword-only in spirit; defaults keep the reference behaviour) ----
             noise_mode: Optional[str] = None,     # 'philox' | 'injected' | 'off'
-            engine: str = "auto",                 # 'auto' | 'runahead' | 'persistent' | 'stepwise'
+            engine: str = "auto",                 # 'auto' | 'fixpoint' | 'runahead' | 'persistent' | 'stepwise'
             voxel_dtype: torch.dtype = torch.float32,
             philox_rounds: int = 10,
             normalize: bool = True,
@@ -252,7 +252,8 @@ class EventEmulator(nn.Module):
             cfg.output_mode = _cabi.OUT_VOXEL if self.normalize else _cabi.OUT_VOXEL_UNNORM
         cfg.engine = {"auto": _cabi.ENGINE_AUTO, "stepwise": _cabi.ENGINE_STEPWISE,
                       "persistent": _cabi.ENGINE_PERSISTENT,
-                      "runahead": _cabi.ENGINE_RUNAHEAD}[self.engine]
+                      "runahead": _cabi.ENGINE_RUNAHEAD,
+                      "fixpoint": _cabi.ENGINE_FIXPOINT}[self.engine]
         f32 = torch.float32
         cfg.leak_rate = float(torch.tensor(self.leak_rate_hz, dtype=f32))
         cfg.leak_jitter = float(torch.tensor(self.leak_jitter_fraction, dtype=f32))
@@ -282,6 +283,9 @@ class EventEmulator(nn.Module):
         if status == _cabi.STATUS_NONINTEGER_FRAMES:
             raise ValueError("integer_frames=True was asserted but a frame value is not an "
                              "integer in 0..255: the outputs of this pack are invalid")
+        if status == _cabi.STATUS_NOT_CONVERGED:
+            raise RuntimeError("fixed-point engine: the per-frame maxima did not settle "
+                               "(internal error): the outputs of this pack are invalid")
 
     def check_status(self) -> None:
         """Raise if the last pack reported a contract violation (synchronises)."""
@@ -295,7 +299,8 @@ class EventEmulator(nn.Module):
             return None
         return {_cabi.ENGINE_STEPWISE: "stepwise",
                 _cabi.ENGINE_PERSISTENT: "persistent",
-                _cabi.ENGINE_RUNAHEAD: "runahead"}.get(self._launch.resolve_engine())
+                _cabi.ENGINE_RUNAHEAD: "runahead",
+                _cabi.ENGINE_FIXPOINT: "fixpoint"}.get(self._launch.resolve_engine())
 
     def forward(self, frames, t_frames):
         """Compute events based on a sequence of frames (v2e_model.py:290-536).
