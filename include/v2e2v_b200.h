@@ -215,6 +215,17 @@ int v2e_host_pack_scalars(const v2e_host_params* hp, const double* t_frames,
 int v2e_pack_forward(const v2e_config* cfg, const v2e_pack* packs, int n_seq,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* -- a clip: consecutive packs of ONE sequence in one call --------------------------------------
+ * Replaces the Python loop `for pack in clip: emulator(pack_frames, pack_stamps)` around
+ * EventEmulator.forward (test.py:115-121 / model_v2e2v.py:101 drive it that way): packs[i+1]
+ * continues from the state packs[i] leaves, so all entries name the same state planes and are
+ * launched in order on `stream`, one launch each, with no host work in between.  Each pack has
+ * its own frames / voxel / num_events / status / scalars (v2e_host_pack_scalars, prepared ahead).
+ * events: optional array of 2*n_packs cudaEvent_t, recorded before and after each pack's launch
+ * (NULL: none).  Same workspace rules as v2e_pack_forward. */
+int v2e_clip_forward(const v2e_config* cfg, const v2e_pack* packs, int n_packs,
+                     void* workspace, size_t workspace_bytes, void* stream, void* const* events);
+
 /* -- standalone event -> voxel grid (utils/event_process.py:15-63 / 66-129) ------------------
  * events: device f32 or f64 [n,4] rows (t,x,y,p), time-sorted.  Unlike the reference this does
  * NOT mutate `events`.  voxel: device f32 [num_bins,H,W], overwritten.  t_first/t_last are

@@ -23,7 +23,7 @@ for k, fr, tfr in gc.video(1, 5, T, H, W):
     npass = int(tl[0, 30])
     us = lambda a: (a - t0) / 1e3
     print(f"pack {k}: CTAs {tl.shape[0]} passes {npass}  entries/tile mean {tl[:,28].mean():.0f} max {tl[:,28].max()} "
-          f"spill mean {tl[:,29].mean():.1f} max {tl[:,29].max()}")
+          f"spill mean {tl[:,29].mean():.1f} max {tl[:,29].max()} heavy mean {tl[:,26].mean():.0f}")
     rows = [("start", 0), ("setup done", 1), ("pass1 done", 2)]
     for ps in range(min(npass, 8)):
         rows += [(f"resolve{ps} done", 3 + 3 * ps), (f"barrier{ps} done", 4 + 3 * ps)]

@@ -88,7 +88,8 @@ def test_constants_match_header():
               "ERR_WORKSPACE", "ERR_NO_DEVICE", "NOISE_OFF", "NOISE_INJECTED", "NOISE_PHILOX",
               "DT_F32", "DT_U8", "DT_BF16", "OUT_VOXEL", "OUT_RAW", "OUT_VOXEL_UNNORM",
               "ENGINE_AUTO", "ENGINE_STEPWISE", "ENGINE_PERSISTENT",
-              "ENGINE_RUNAHEAD", "STATUS_OK", "STATUS_NONINTEGER_FRAMES"):
+              "ENGINE_RUNAHEAD", "ENGINE_FIXPOINT", "STATUS_OK", "STATUS_NONINTEGER_FRAMES",
+              "STATUS_NOT_CONVERGED"):
         assert int(defs["V2E_" + k]) == getattr(_cabi, k), k
 
 

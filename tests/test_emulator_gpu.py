@@ -196,6 +196,35 @@ def test_full_size_1280x720_properties():
         assert abs(v.mean().item()) < 1e-4 and abs(v.std(unbiased=False).item() - 1) < 1e-4
 
 
+@pytest.mark.parametrize("fdt", [torch.float32, torch.uint8])
+def test_forward_clip_equals_pack_loop(fdt):
+    """forward_clip (one C call, K launches) == K calls of forward(): states, counts and voxel
+    grids bit-identical (same Philox stream: the pack counter advances the same way)."""
+    cfg, H, W, T, K = gc.CFG2, 96, 160, 10, 6
+    pos, neg, nra = gc.make_planes(23, H, W, cfg)
+    vids = [(fr.to(fdt).cuda(), tfr) for _, fr, tfr in gc.video(8, K, T, H, W)]
+    res = []
+    for clip in (False, True):
+        em = gc.cuda_emulator(cfg, "auto", noise_mode="philox")
+        em.philox_seed = 99
+        em.set_planes(pos, neg, nra)
+        if clip:
+            vox, nev = em.forward_clip([v[0] for v in vids[:4]], [v[1] for v in vids[:4]])
+            vox2, nev2 = em.forward_clip(torch.cat([v[0] for v in vids[4:]]), [v[1] for v in vids[4:]])
+            em.check_status()
+            vox, nev = torch.cat([vox, vox2]), torch.cat([nev, nev2]).tolist()
+        else:
+            outs = [em(fr, tfr) for fr, tfr in vids]
+            vox, nev = torch.cat([o[0] for o in outs]), [o[1] for o in outs]
+        res.append((vox.cpu().numpy(), nev, em.base_log_frame.cpu().numpy(),
+                    em.timestamp_mem.cpu().numpy(), em.t_previous))
+    a, b = res
+    assert a[1] == b[1] and a[4] == b[4]
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+
+
 def test_time_order_error_and_reset():
     em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
     fr = torch.randint(0, 255, (1, 4, 16, 16)).float().cuda()
@@ -265,4 +294,8 @@ def test_runahead_integer_frames_contract():
 def test_auto_engine_is_fastest_known():
     em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
     em(torch.zeros(1, 4, 64, 64, device="cuda"), torch.tensor([[0.0, 0.003]], dtype=torch.float64))
-    assert em.resolved_engine == "persistent"
+    assert em.resolved_engine == "fixpoint"
+    raw = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0, output_mode="raw"),
+                           "auto")
+    raw(torch.zeros(1, 4, 64, 64, device="cuda"), torch.tensor([[0.0, 0.003]], dtype=torch.float64))
+    assert raw.resolved_engine == "persistent"

@@ -152,6 +152,8 @@ SYMBOLS = {
                                         C.POINTER(C.c_float), C.POINTER(PackScalars)]),
     "v2e_pack_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Pack), C.c_int,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    "v2e_clip_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Pack), C.c_int,
+                                   C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
     "v2e_events_to_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_double, C.c_double, C.c_int,
                                       C.c_void_p, C.c_void_p]),
@@ -161,7 +163,8 @@ SYMBOLS = {
 
 LIB_NAME = "libv2e2v_b200.so"
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, LIB_NAME)
+# V2E_LIB: development aid (kernel variants built side by side under v2e2v_b200/_build)
+LIB_PATH = os.environ.get("V2E_LIB") or os.path.join(_PKG_DIR, LIB_NAME)
 
 _lib = None
 _lock = threading.Lock()

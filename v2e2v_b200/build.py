@@ -59,8 +59,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s, o = os.path.join(CSRC, src), os.path.join(BUILD, src + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            r = subprocess.run([_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o], capture_output=True,
-                               text=True)
+            extra = os.environ.get("V2E_NVCC_EXTRA", "").split()   # development aid
+            r = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o],
+                               capture_output=True, text=True)
             log.append(r.stderr)
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr}")

@@ -123,8 +123,12 @@ int v2e_resolve_engine(const v2e_config* c, int n_seq) {
         if (ra < 0) return ra;
         return ra ? V2E_ENGINE_RUNAHEAD : V2E_ERR_UNSUPPORTED;
     }
-    // AUTO: the lock-step persistent engine is the faster one on B200 today (DESIGN.md,
-    // "Engines"); the run-ahead engine is opt-in.
+    // AUTO: the fixed-point engine serves the voxel modes (fastest on B200, DESIGN.md "Engines");
+    // raw event rows go to the lock-step persistent engine; the run-ahead engine is opt-in.
+    if (c->engine == V2E_ENGINE_AUTO && cfg.output_mode != V2E_OUT_RAW) {
+        const int fx = fixpoint_fits(cfg, c->frame_dtype, n_seq);
+        if (fx > 0) return V2E_ENGINE_FIXPOINT;
+    }
     const int fits = persistent_fits(cfg, c->frame_dtype, n_seq);
     if (fits < 0) return fits;
     if (c->engine == V2E_ENGINE_PERSISTENT) return fits ? V2E_ENGINE_PERSISTENT : V2E_ERR_UNSUPPORTED;
@@ -158,6 +162,25 @@ int v2e_pack_forward(const v2e_config* c, const v2e_pack* packs, int n_seq, void
     if (engine == V2E_ENGINE_PERSISTENT)
         return run_persistent(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
     return run_stepwise(cfg, c->frame_dtype, rounds, packs, n_seq, workspace, st);
+}
+
+int v2e_clip_forward(const v2e_config* c, const v2e_pack* packs, int n_packs, void* workspace,
+                     size_t workspace_bytes, void* stream, void* const* events) {
+    if (!packs || n_packs < 1) return V2E_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n_packs; ++i) {
+        if (events && events[2 * i]) {
+            const int rc = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i], st));
+            if (rc != V2E_OK) return rc;
+        }
+        const int rc = v2e_pack_forward(c, packs + i, 1, workspace, workspace_bytes, stream);
+        if (rc != V2E_OK) return rc;
+        if (events && events[2 * i + 1]) {
+            const int rc2 = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i + 1], st));
+            if (rc2 != V2E_OK) return rc2;
+        }
+    }
+    return V2E_OK;
 }
 
 }  // extern "C"

@@ -9,7 +9,10 @@
 namespace v2e {
 
 constexpr int kMaxPartials = 2048;
-constexpr size_t kTimelineBytes = 160 * 32 * 8;  // development aid: [cta][32] clock stamps
+constexpr size_t kTimelineBytes = 160 * 32 * 8 + 2048;  // development aid: [cta][32] clock stamps + [128][2] launch start/end ring
+// fixed-point engine: ring of launch records for multi-sequence launches (8 slots x 16 sequences
+// x (SeqDev + 32 FrameSc) <= 8 * 16 * 1280 bytes)
+constexpr size_t kFxBlkBytes = 8 * 16 * 1280;
 constexpr int kRaMaxTiles = 160;  // run-ahead engine: tiles (CTAs) per sequence, <= SM count
 
 // Per-sequence work area inside the caller's workspace.  Zero on entry, zero on exit.
@@ -41,7 +44,7 @@ struct FxWork {
 };
 
 struct StepLayout {
-    size_t work_off, vox_off, cntpol_off, fx_off, fxstate_off, tl_off, total;
+    size_t work_off, vox_off, cntpol_off, fx_off, fxstate_off, fxblk_off, tl_off, total;
     int n_partials;
 };
 
@@ -53,7 +56,8 @@ inline StepLayout step_layout(const CfgDev& cfg, int n_seq) {
     l.cntpol_off = up(l.vox_off + (size_t)n_seq * cfg.nb * cfg.P * sizeof(float));
     l.fx_off = up(l.cntpol_off + (size_t)n_seq * cfg.P * sizeof(int));
     l.fxstate_off = up(l.fx_off + sizeof(FxWork) * (size_t)n_seq);
-    l.tl_off = up(l.fxstate_off + (size_t)n_seq * 3 * cfg.P * sizeof(float));
+    l.fxblk_off = up(l.fxstate_off + (size_t)n_seq * 3 * cfg.P * sizeof(float));
+    l.tl_off = up(l.fxblk_off + kFxBlkBytes);
     l.total = up(l.tl_off + kTimelineBytes);
     const size_t N = (size_t)cfg.nb * cfg.P;
     size_t np = (N + 256 * 16 - 1) / (256 * 16);

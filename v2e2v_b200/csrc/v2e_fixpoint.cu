@@ -27,7 +27,7 @@
 //   commit            normalise (utils/event_process.py:157-177) and scatter the entries' voxel
 //                     columns and state.
 //
-// Statistics are accumulated as exact integers (voxel values are multiples of 2^-33 in all
+// Statistics are accumulated as exact integers (voxel values are multiples of 2^-31 in all
 // practical cases: fixed point, 64-bit sum and 128-bit sum of squares), so they do not depend
 // on the order in which lanes, warps and tiles add them: results are run-to-run deterministic.
 //
@@ -42,37 +42,67 @@
 namespace v2e {
 
 #ifndef V2E_FX_THREADS
-#define V2E_FX_THREADS 512
+#define V2E_FX_THREADS 768
 #endif
 constexpr int kFxThreads = V2E_FX_THREADS;
 constexpr int kFxWarps = kFxThreads / 32;
 constexpr int kFxChunk = 10;        // frames per unrolled chunk = frames per Philox block
 constexpr int kFxHeader = 4096;     // LUT, frame tables, reduction scratch
 constexpr int kFxSpin = 1 << 25;    // barrier poll limit (a lost CTA must not hang the GPU)
+// Specialised variants (SPEC): the reference's pack shape (10 frames, 5 bins) with everything the
+// address arithmetic needs known at compile time, for the 227 KB of shared memory a B200 CTA gets.
+constexpr int kFxSpecT = 10, kFxSpecNb = 5, kFxSpecSmem = 232448;
 
-// entry words (structure of arrays: word w of entry e lives at s_ent[w * cap + e])
+// entry words (structure of arrays: word w of entry e lives at s_ent[w * cap + e]).  After the
+// fixed words come num_bins voxel accumulators, then per frame k = n-1 < 10 the two inputs of the
+// pixel that no event can change: nw (the low-passed log intensity the frame presents,
+// v2e_model.py:375) and, with leak on, dl (the leak decrement of that frame,
+// emulator_utils.py:117-125).
 enum {
-    FX_META = 0,   // [4:0] first active frame f, [5] timestamp_mem == 0 (else -Tr), [31:8] tile-local pixel
-    FX_BASE, FX_LP, FX_POS, FX_NEG, FX_NLK,
-    FX_F0, FX_F1, FX_F2,   // frame bytes 1..10 (frame n in byte n-1)
-    FX_OB, FX_OT,          // results: base_log_frame, timestamp_mem
-    FX_V0                  // results: num_bins voxel accumulators
+    FX_META = 0,   // [4:0] first active frame f, [5] timestamp_mem == 0 (else -Tr), [15:6] frames
+                   // that may hold a shot-noise event (conservative first-stage test)
+    FX_IDX,        // tile-local pixel index
+    FX_BASE,       // base_log_frame before frame f
+    FX_POS, FX_NEG,
+    FX_OB, FX_OT,  // results: base_log_frame, timestamp_mem
+    FX_V0          // results: num_bins voxel accumulators
 };
 
+// one sequence's launch record: device descriptor + per-frame scalars
+struct FxSeqBlock {
+    SeqDev sq;
+    FrameSc fr[V2E_MAX_FRAMES];
+};
+constexpr int kFxBlkRing = 8;   // launches whose records may be in flight in the workspace
+static_assert(sizeof(FxSeqBlock) <= 1280 && kFxBlkRing * V2E_MAX_SEQ_PER_LAUNCH * 1280 <= kFxBlkBytes,
+              "workspace ring too small (v2e_engine.cuh, kFxBlkBytes)");
+
+// Kernel parameters stay well under 4 KB: the launch path for larger parameter blocks costs
+// ~20 us per launch on this driver (measured: scripts/clip_probe.py), more than a barrier pass.
 struct FxParams {
     CfgDev cfg;
     int n_seq;
     int tiles_per_seq;
     int tile_px;       // pixels per tile, multiple of 32
     int cap;           // compact entries per tile, multiple of 32
+    int nw_off, dl_off;  // entry word offsets of the per-frame inputs
     FxWork* fx;        // [n_seq]
     unsigned* spill_list;  // [n_seq][P]   tile-local indices of spilled pixels, per tile region
     float* spill_vox;      // [n_seq][nb][P] voxel accumulators of spilled pixels
     float* spill_state;    // [n_seq][3][P]  base, lp, tmem results of spilled pixels
     long long* timeline;   // development aid (V2E_TIMELINE=1): [cta][32] globaltimer stamps
-    SeqDev seq[V2E_MAX_SEQ_PER_LAUNCH];
-    FrameSc fr[V2E_MAX_SEQ_PER_LAUNCH][V2E_MAX_FRAMES];
+    const FxSeqBlock* blocks;   // n_seq > 1: records in the workspace (copied there in stream order)
+    FxSeqBlock one;             // n_seq == 1: the record travels with the parameters
 };
+static_assert(sizeof(FxParams) < 4000, "keep the kernel parameters on the fast launch path");
+static_assert(sizeof(SeqDev) <= 240, "SeqDev must fit its shared-memory slot");
+
+__host__ __device__ constexpr int fx_spec_ewords(bool leak) {
+    return FX_V0 + kFxSpecNb + (kFxSpecT - 1) * (leak ? 2 : 1);
+}
+__host__ __device__ constexpr int fx_spec_cap(bool leak) {
+    return ((kFxSpecSmem - kFxHeader) / (4 * fx_spec_ewords(leak))) & ~31;
+}
 
 // ---- memory-ordering helpers ---------------------------------------------------------------------
 __device__ __forceinline__ void fx_st_release(unsigned* p, unsigned v) {
@@ -101,6 +131,7 @@ __device__ __forceinline__ long long fx_now() {
 //   A: 4 words -> 8 normals (Box-Muller pairs), frames +1..+8
 //   B: .x .y .z -> 12 bytes, first stage of the shot test of frames +1..+10 (+2 spare);
 //      .w -> normals of frames +9, +10
+// A pack of T <= 11 frames is one block: two calls per pixel and pack.
 // (The lock-step engines index their stage-0 stream by (4-pixel group, frame); a pixel that is
 // resolved on its own would waste 3/4 of every call.  The second-stage streams are shared.)
 template <int R>
@@ -110,12 +141,17 @@ __device__ __forceinline__ uint4 noise_px(unsigned long long ctr64, unsigned p, 
         make_uint4(p, c | ((0x80u + which) << 8), (unsigned)ctr64, (unsigned)(ctr64 >> 32)));
 }
 
-// exact integer statistics of one voxel value: v = k * 2^-33 (truncated if finer, never in practice)
+// exact integer statistics of one voxel value: v = k * 2^-31.  Voxel values are sums of a few
+// pol*(1-d), pol*d with d a fraction of an f32 time stamp in [0, num_bins): multiples of 2^-31
+// whenever |v| >= 2^-8 (finer bits, if any, are truncated - the same way in every order).
+// integer part and fraction are split exactly (Sterbenz), so no 64-bit conversion is needed.
 __device__ __forceinline__ void fx_stat(float v, unsigned& nnz, long long& s1,
                                         unsigned long long& lo, unsigned long long& hi) {
     if (v != 0.f) {
         nnz += 1;
-        const long long k = __float2ll_rz(v * 8589934592.0f);
+        const int ip = __float2int_rz(v);                         // |v| < 2^31 always (event counts)
+        const int fp = __float2int_rz((v - (float)ip) * 2147483648.0f);
+        const long long k = ((long long)ip << 31) + (long long)fp;
         s1 += k;
         const unsigned long long a = (unsigned long long)(k < 0 ? -k : k);
         const unsigned long long plo = a * a;
@@ -148,102 +184,315 @@ struct FxAcc {   // per-lane accumulators of a resolve pass
     unsigned long long lo, hi;
 };
 
-// ---- resolve one pixel from frame f under the current guess ---------------------------------------
-// getLI(k) -> (lin_log, inten01) of frame k+1; vp/vstride: the pixel's voxel accumulators.
-// All lanes of the warp call this together (the per-frame max is a warp reduction); `on` masks
-// lanes without an entry.
-template <int FDT, int R, bool GENERIC, class GetLI>
-__device__ __forceinline__ void fx_resolve(const FxParams& prm, const SeqDev& sq, bool on, int p,
-                                           int f, float& base, float& lp, float& tm, float pos,
-                                           float neg, float nlk, bool small, bool leak, bool shot,
-                                           bool philox, bool cutoff, const FrameSc* s_fr,
-                                           const FrameGlobals* s_g, unsigned* s_max, float* vp,
-                                           int vstride, FxAcc& acc, GetLI getLI) {
+
+// leak decrement of one frame: (sdt*((leak*nra)*(1 - jit*z)))*pos   (emulator_utils.py:117-125)
+__device__ __forceinline__ float leak_dec(float lk_nra, float jit, float z, float sdt, float pos) {
+    return fmul(fmul(sdt, fmul(lk_nra, fsub(1.0f, fmul(jit, z)))), pos);
+}
+
+// per-CTA view of the shared-memory header
+struct FxSmem {
+    float2* lut;
+    FrameSc* fr;
+    FrameGlobals* g;
+    unsigned* max;
+    unsigned long long* acc;
+};
+
+// tile partials -> shared memory (integer adds: order-free)
+__device__ __forceinline__ void fx_flush(const FxAcc& acc, unsigned long long* s_acc) {
+    unsigned long long nnz = acc.nnz, nev = acc.nev, lo = acc.lo, hi = acc.hi;
+    long long s1 = acc.s1;
+    for (int o = 16; o > 0; o >>= 1) {
+        nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
+        nev += __shfl_xor_sync(0xffffffffu, nev, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        const unsigned long long olo = __shfl_xor_sync(0xffffffffu, lo, o);
+        const unsigned long long ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo += olo;
+        hi += ohi + (lo < olo ? 1ull : 0ull);
+    }
+    if ((threadIdx.x & 31) == 0 && (nnz | nev)) {
+        atomicAdd(&s_acc[0], nnz);
+        atomicAdd(&s_acc[1], (unsigned long long)s1);
+        const unsigned long long old = atomicAdd(&s_acc[2], lo);
+        atomicAdd(&s_acc[3], hi + (old + lo < old ? 1ull : 0ull));
+        atomicAdd(&s_acc[4], nev);
+    }
+}
+
+// ---- event frame of one pixel under the current guess: the general case, out of line ---------------
+// (shot-noise candidates, injected draws, gate off).  cnt/pol/C: diff_count results of frame n;
+// bit: the frame may hold a shot event (I is read back from the frame only then).  Everything
+// goes in and out by value (an address-taken local would live in local memory, and with the
+// whole L1 carved out as shared memory that is an L2 round trip per access).
+// Returns (final_evts_frame << 32) | bits(timestamp_mem).
+template <int FDT, int R, bool GENERIC>
+static __device__ __noinline__ unsigned long long fx_event_frame(
+    const FxParams& prm, const SeqDev& sq, const FxSmem sm, int n, int p, int cnt, float pol,
+    float C, bool bit, bool shot, bool philox, float tm, float* vp, int vstride) {
     const CfgDev& cfg = prm.cfg;
-    const int T = sq.T, P = cfg.P;
-    const int lane = threadIdx.x & 31;
-    const int nchunks = (T - 1 + kFxChunk - 1) / kFxChunk;
-    for (int c = 0; c < nchunks; ++c) {
-        const int n0 = 1 + c * kFxChunk;
-        uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
-        if (philox && on) {
-            if (leak) wa = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 0);
-            if (shot || (leak && T - n0 > 8)) wb = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 1);
-        }
-        float z0 = 0.f, z1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < kFxChunk; ++k) {
-            const int n = n0 + k;
-            if (n >= T) break;
-            const FrameSc& fs = s_fr[n];
-            const bool act = on && n >= f;
-            int cnt = 0;
-            float pol = 0.f, C = 0.f, I = 0.f, z = 0.f;
-            if (leak && philox && (k & 1) == 0) box_muller16(k < 8 ? (&wa.x)[k >> 1] : wb.w, z0, z1);
-            if (act) {
-                const float2 li = getLI(n);
-                I = li.y;
-                float nw = li.x;
-                if (cutoff) {
-                    lp = lowpass(lp, li.x, I, small ? fs.s_small : fs.s_large);
-                    nw = lp;
-                }
-                if (leak) {
-                    z = philox ? ((k & 1) ? z1 : z0) : __ldg(sq.leak_randn + (size_t)(n - 1) * P + p);
-                    base = leak_sub(base, nlk, cfg.leak_jitter, z, fs.sdt, pos);
-                }
-                const PixelA a = diff_count(nw, base, pos, neg);
-                cnt = a.cnt;
-                pol = a.pol;
-                C = a.C;
+    const FrameSc& fs = sm.fr[n];
+    const FrameGlobals g = sm.g[n];
+    bool cand = false;
+    float u = 0.f, I = 0.f;
+    if (shot && bit && pol != 0.f) {
+        float L;
+        log_inten(sm.lut, load_frame1<FDT>(sq.frames, (long long)n * cfg.P + p), L, I);
+        if (philox) {
+            const int k = (n - 1) % kFxChunk;
+            const uint4 wb = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)((n - 1) / kFxChunk), 1);
+            const unsigned w = k < 4 ? wb.x : (k < 8 ? wb.y : wb.z);
+            const unsigned byte = (w >> (8 * (k & 3))) & 0xffu;
+            const float thr256 = shot_thr256(pol > 0.f ? fs.kp : fs.kn, cfg.shot_inten_m1, I, C);
+            if ((float)byte < thr256) {
+                u = shot_uniform<R>(sq.philox_ctr, n, p, byte);
+                cand = u * 256.0f < thr256;
             }
-            const int wm = __reduce_max_sync(0xffffffffu, cnt);
-            if (lane == 0 && wm > 0) atomicMax(&s_max[n], (unsigned)wm);
-            if (act) {
-                const FrameGlobals g = s_g[n];
-                const bool live = pol != 0.f;
-                bool cand = false;
-                float u = 0.f;
-                if (shot && live) {
-                    if (philox) {
-                        const float thr256 = shot_thr256(pol > 0.f ? fs.kp : fs.kn, cfg.shot_inten_m1, I, C);
-                        const unsigned byte = ((&wb.x)[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                        if ((float)byte < thr256) {
-                            u = shot_uniform<R>(sq.philox_ctr, n, p, byte);
-                            cand = u * 256.0f < thr256;
-                        }
-                    } else {
-                        cand = true;   // injected draws: every pol != 0 pixel walks the iterations
+        } else {
+            cand = true;   // injected draws: every pol != 0 pixel walks the iterations
+        }
+    }
+    if (cnt > 0 || cand) {
+        const int mode = (cand && g.mx > 0) ? (philox ? 2 : 1) : 0;
+        return fx_events<R>(&prm.cfg, &sq, &fs, g.mx, g.ts_step, g.gate, n, p, pol, C,
+                            min(cnt, g.mx), I, tm, mode, u, vp, vstride);
+    }
+    return (unsigned long long)__float_as_uint(tm);
+}
+
+template <bool GENERIC>
+__device__ __forceinline__ void fx_dbg(const SeqDev& sq, int P, int n, int p, float pol, int cnt,
+                                       int fin) {
+    if (GENERIC) {
+        const size_t o = (size_t)(n - 1) * P + p;
+        if (sq.dbg_pol) sq.dbg_pol[o] = (signed char)pol;
+        if (sq.dbg_cnt) sq.dbg_cnt[o] = cnt;
+        if (sq.dbg_final) sq.dbg_final[o] = fin;
+    }
+}
+
+template <bool GENERIC>
+__device__ __forceinline__ void fx_dbg_clear_shot(const SeqDev& sq, int P, int p, int f, int T) {
+    // an earlier pass (under another guess) may have marked other iterations
+    if (GENERIC && sq.dbg_shot)
+        for (int n = f; n < T; ++n)
+            for (int i = 0; i < sq.dbg_shot_imax; ++i)
+                sq.dbg_shot[((size_t)(n - 1) * sq.dbg_shot_imax + i) * P + p] = 0;
+}
+
+// ---- spilled pixels: inputs re-read from global memory, results kept in the workspace -------------
+// Frame-synchronous, one pixel per lane, everything recomputed from the pack's first frame.
+template <int FDT, int R, bool GENERIC, bool SPEC>
+static __device__ __noinline__ void fx_resolve_spill(const FxParams& prm, const SeqDev& sq,
+                                                     FxSmem sm, const unsigned* spill_list,
+                                                     int n_spill, int tile_px0, float* spill_vox,
+                                                     float* spill_state, bool leak, bool shot,
+                                                     bool philox, bool cutoff) {
+    const CfgDev& cfg = prm.cfg;
+    const int T = SPEC ? kFxSpecT : sq.T, P = cfg.P, nb = SPEC ? kFxSpecNb : cfg.nb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FxAcc acc;
+    acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
+    for (int e0 = warp * 32; e0 < n_spill; e0 += kFxThreads) {
+        const int e = e0 + lane;
+        const bool on = e < n_spill;
+        const int p = tile_px0 + (on ? (int)spill_list[e] : 0);
+        float base, lp = 0.f, tm;
+        const float pos = __ldg(sq.pos + p), neg = __ldg(sq.neg + p);
+        const float nlk = leak ? fmul(cfg.leak_rate, __ldg(sq.nra + p)) : 0.f;
+        if (sq.first_pack) {
+            float L0, I0;
+            log_inten(sm.lut, load_frame1<FDT>(sq.frames, p), L0, I0);
+            base = L0;
+            lp = L0;
+            tm = fadd(0.f, -sq.Tr);
+        } else {
+            base = sq.base[p];
+            if (cutoff) lp = sq.lp[p];
+            tm = sq.tmem[p];
+            if (tm > 0.f) tm = fsub(tm, sq.bins_m1);
+            if (tm < 0.f) tm = -sq.Tr;
+        }
+        float* vp = spill_vox + p;
+        if (on) {
+            for (int b = 0; b < nb; ++b) vp[(size_t)b * P] = 0.f;
+            fx_dbg_clear_shot<GENERIC>(sq, P, p, 1, T);
+        }
+        const bool small = is_small_px(p, cfg.W);
+        const int nchunks = (T - 1 + kFxChunk - 1) / kFxChunk;
+        for (int c = 0; c < nchunks; ++c) {
+            const int n0 = 1 + c * kFxChunk;
+            uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+            if (philox && leak) {
+                wa = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 0);
+                if (T - n0 > 8) wb = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 1);
+            }
+            float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kFxChunk; ++k) {
+                const int n = n0 + k;
+                if (n >= T) break;
+                const FrameSc& fs = sm.fr[n];
+                if (leak && philox && (k & 1) == 0) box_muller16(k < 8 ? (&wa.x)[k >> 1] : wb.w, z0, z1);
+                int cnt = 0;
+                if (on) {
+                    float L, I;
+                    log_inten(sm.lut, load_frame1<FDT>(sq.frames, (long long)n * P + p), L, I);
+                    float nw = L;
+                    if (cutoff) {
+                        lp = lowpass(lp, L, I, small ? fs.s_small : fs.s_large);
+                        nw = lp;
                     }
-                }
-                int fin = 0;
-                if (GENERIC && sq.dbg_shot)
-                    for (int i = 0; i < sq.dbg_shot_imax; ++i)
-                        sq.dbg_shot[((size_t)(n - 1) * sq.dbg_shot_imax + i) * P + p] = 0;
-                if (cnt > 0 || cand) {
-                    const int mode = (cand && g.mx > 0) ? (philox ? 2 : 1) : 0;
-                    const unsigned long long r = fx_events<R>(
-                        &prm.cfg, &sq, &fs, g.mx, g.ts_step, g.gate, n, p, pol, C, min(cnt, g.mx),
-                        I, tm, mode, u, vp, vstride);
-                    fin = (int)(r >> 32);
+                    if (leak) {
+                        const float z = philox ? ((k & 1) ? z1 : z0)
+                                               : __ldg(sq.leak_randn + (size_t)(n - 1) * P + p);
+                        base = fsub(base, leak_dec(nlk, cfg.leak_jitter, z, fs.sdt, pos));
+                        if (GENERIC && sq.dbg_leak_randn && philox)
+                            sq.dbg_leak_randn[(size_t)(n - 1) * P + p] = z;
+                    }
+                    const PixelA a = diff_count(nw, base, pos, neg);
+                    cnt = a.cnt;
+                    if ((unsigned)cnt > sm.max[n]) atomicMax(&sm.max[n], (unsigned)cnt);
+                    const unsigned long long r = fx_event_frame<FDT, R, GENERIC>(
+                        prm, sq, sm, n, p, cnt, a.pol, a.C, true, shot, philox, tm, vp, P);
+                    const int fin = (int)(r >> 32);
                     tm = __uint_as_float((unsigned)r);
                     if (fin) {
                         acc.nev += (unsigned)fin;
-                        base = fadd(base, fmul(fmul(pol, (float)fin), C));   // v2e_model.py:522
+                        base = fadd(base, fmul(fmul(a.pol, (float)fin), a.C));   // v2e_model.py:522
                     }
-                }
-                if (GENERIC) {
-                    const size_t o = (size_t)(n - 1) * P + p;
-                    if (sq.dbg_pol) sq.dbg_pol[o] = (signed char)pol;
-                    if (sq.dbg_cnt) sq.dbg_cnt[o] = cnt;
-                    if (sq.dbg_final) sq.dbg_final[o] = fin;
-                    if (sq.dbg_leak_randn && leak && philox) sq.dbg_leak_randn[o] = z;
+                    fx_dbg<GENERIC>(sq, P, n, p, a.pol, cnt, fin);
                 }
             }
         }
+        if (on) {
+            spill_state[p] = base;
+            spill_state[(size_t)P + p] = lp;
+            spill_state[(size_t)2 * P + p] = tm;
+            for (int b = 0; b < nb; ++b) fx_stat(vp[(size_t)b * P], acc.nnz, acc.s1, acc.lo, acc.hi);
+        }
     }
-    if (on)
-        for (int b = 0; b < cfg.nb; ++b) fx_stat(vp[(size_t)b * vstride], acc.nnz, acc.s1, acc.lo, acc.hi);
+    fx_flush(acc, sm.acc);
+}
+
+// ---- compact entries: frame-synchronous, one entry per lane ------------------------------------------
+// Per frame an entry costs two shared-memory loads, two subtractions, the threshold test and the
+// quotient; the event code behind it is reached by the lanes that cross (about one in eight).
+template <int FDT, int R, int NOISE, bool SPEC>
+static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, const SeqDev& sq,
+                                                       FxSmem sm, unsigned* s_ent, int n_ent,
+                                                       int* task_ctr, int tile_px0, bool leak_rt,
+                                                       bool shot_rt, bool philox_rt) {
+    constexpr bool GENERIC = NOISE == 2;
+    constexpr bool LEAKC = NOISE == 1;
+    const bool leak = GENERIC ? leak_rt : (NOISE == 1);
+    const bool shot = GENERIC ? shot_rt : (NOISE == 1);
+    const bool philox = GENERIC ? philox_rt : (NOISE == 1);
+    const CfgDev& cfg = prm.cfg;
+    const int T = SPEC ? kFxSpecT : sq.T, P = cfg.P, nb = SPEC ? kFxSpecNb : cfg.nb;
+    const int cap = SPEC ? fx_spec_cap(LEAKC) : prm.cap;
+    const int nw_off = SPEC ? FX_V0 + kFxSpecNb : prm.nw_off;
+    const int dl_off = SPEC ? FX_V0 + kFxSpecNb + kFxSpecT - 1 : prm.dl_off;
+    const int lane = threadIdx.x & 31;
+    const float Tr = sq.Tr;
+    FxAcc acc;
+    acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
+    const int ntasks = (n_ent + 31) >> 5;
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(task_ctr, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntasks) break;
+        const int e = t * 32 + lane;
+        const bool on = e < n_ent;
+        unsigned* ep = s_ent + (on ? e : 0);
+        const unsigned meta = ep[FX_META * cap];
+        const int p = tile_px0 + (int)ep[FX_IDX * cap];
+        const unsigned cm = (meta >> 6) & 0x3ffu;
+        float base = __uint_as_float(ep[FX_BASE * cap]);
+        float tm = (meta & 32u) ? 0.f : -Tr;
+        const float pos = __uint_as_float(ep[FX_POS * cap]);
+        const float neg = __uint_as_float(ep[FX_NEG * cap]);
+        float* vp = (float*)(ep + FX_V0 * cap);
+        const float* nwp = (const float*)(ep + (nw_off - 1) * cap);   // [n] -> frame n
+        const float* dlp = (const float*)(ep + (dl_off - 1) * cap);
+        const int f = on ? (int)(meta & 31u) : V2E_MAX_FRAMES;
+        if (on) {
+#pragma unroll
+            for (int b = 0; b < (SPEC ? kFxSpecNb : V2E_MAX_BINS); ++b)
+                if (b < nb) vp[b * cap] = 0.f;
+            fx_dbg_clear_shot<GENERIC>(sq, P, p, f, T);
+        }
+#pragma unroll 1
+        for (int n = 1; n < T; ++n) {   // not unrolled: the loop body should stay in the L0 I-cache
+            const bool act = n >= f;
+            const float b = leak ? fsub(base, dlp[n * cap]) : base;
+            const float diff = fsub(nwp[n * cap], b);
+            const float ad = fabsf(diff);
+            const bool live = act && ad > 1e-6f;   // v2e_model.py:394-395
+            const bool up = diff > 0.f;
+            const float C = live ? (up ? pos : neg) : 0.f;
+            const float den = fadd(C, 1e-9f);
+            const bool cross = live && ad >= den;
+            if (act) base = b;
+            const int cnt = cross ? (int)floorf(fdiv(ad, den)) : 0;   // :404
+            const int wm = __reduce_max_sync(0xffffffffu, cnt);
+            if (lane == 0 && (unsigned)wm > sm.max[n]) atomicMax(&sm.max[n], (unsigned)wm);
+            const bool bit = shot && live && ((cm >> (n - 1)) & 1u);
+            const float pol = live ? (up ? 1.f : -1.f) : 0.f;
+            int fin = 0;
+            if (cross || bit) {
+                const FrameGlobals g = sm.g[n];
+                if (!bit && g.gate) {
+                    // The common event frame, inline: gate on (v2e_model.py:469), no shot draw.
+                    // Iteration j of [0,c) is accepted iff ts_j - timestamp_mem > Tr (:419,:470),
+                    // monotone in j: the next accepted one is the first j that passes.
+                    const float t0 = sm.fr[n].t_bin_prev, step = g.ts_step;
+                    const int c = min(cnt, g.mx);
+                    int i = 0;
+                    while (i < c) {
+                        if (!(fsub(fadd(t0, fmul(step, (float)c)), tm) > Tr)) break;   // none left
+                        int j = i;
+                        if (!(fsub(fadd(t0, fmul(step, (float)(i + 1))), tm) > Tr)) {
+                            j = (int)floorf((Tr + tm - t0) * __fdividef(1.0f, step)) - 1;   // estimate
+                            j = min(max(j, i + 1), c - 1);
+                            while (j < c - 1 && !(fsub(fadd(t0, fmul(step, (float)(j + 1))), tm) > Tr)) ++j;
+                            while (j > i + 1 && fsub(fadd(t0, fmul(step, (float)j)), tm) > Tr) --j;
+                        }
+                        const float ts = fadd(t0, fmul(step, (float)(j + 1)));
+                        tm = ts;
+                        fin += 1;
+                        i = j + 1;
+                        // v2e_model.py:478-502
+                        const float ti = floorf(ts);
+                        const float d = fsub(ts, ti);
+                        const int bb = (int)ti;
+                        if (bb >= 0 && bb < nb) vp[bb * cap] = fadd(vp[bb * cap], fmul(pol, fsub(1.0f, d)));
+                        if (bb >= 0 && bb + 1 < nb) vp[(bb + 1) * cap] = fadd(vp[(bb + 1) * cap], fmul(pol, d));
+                    }
+                } else {
+                    const unsigned long long r = fx_event_frame<FDT, R, GENERIC>(
+                        prm, sq, sm, n, p, cnt, pol, C, bit, shot, philox, tm, vp, cap);
+                    fin = (int)(r >> 32);
+                    tm = __uint_as_float((unsigned)r);
+                }
+                if (fin) {
+                    acc.nev += (unsigned)fin;
+                    base = fadd(base, fmul(fmul(pol, (float)fin), C));   // v2e_model.py:522
+                }
+            }
+            if (act) fx_dbg<GENERIC>(sq, P, n, p, pol, cnt, fin);
+        }
+        if (on) {
+            ep[FX_OB * cap] = __float_as_uint(base);
+            ep[FX_OT * cap] = __float_as_uint(tm);
+#pragma unroll
+            for (int b = 0; b < (SPEC ? kFxSpecNb : V2E_MAX_BINS); ++b)
+                if (b < nb) fx_stat(vp[b * cap], acc.nnz, acc.s1, acc.lo, acc.hi);
+        }
+    }
+    fx_flush(acc, sm.acc);
 }
 
 __device__ __forceinline__ void fx_store_vox(const CfgDev& cfg, void* voxel, size_t o, float v) {
@@ -253,23 +502,37 @@ __device__ __forceinline__ void fx_store_vox(const CfgDev& cfg, void* voxel, siz
 
 // NOISE: 0 = no noise, 1 = PHILOX leak + shot (the V2E2VNet wiring), 2 = generic (every feature
 // decided at run time, debug maps).  CUTOFF is ignored by the generic variant.
-template <int FDT, int R, int NOISE, bool CUTOFF>
+template <int FDT, int R, int NOISE, bool CUTOFF, bool SPEC>
 __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constant__ FxParams prm) {
     constexpr bool GENERIC = NOISE == 2;
+    static_assert(!(SPEC && GENERIC), "the specialised variants have their noise wiring fixed");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const CfgDev& cfg = prm.cfg;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seq = blockIdx.x / prm.tiles_per_seq;
     const int tile = blockIdx.x - seq * prm.tiles_per_seq;
-    const SeqDev& sq = prm.seq[seq];
+    // this sequence's launch record -> shared memory (every later access is an LDS)
+    const FxSeqBlock* blk = prm.blocks ? prm.blocks + seq : &prm.one;
+    {
+        unsigned* d_sq = (unsigned*)(smem_raw + 3840);
+        const unsigned* s_sq = (const unsigned*)&blk->sq;
+        for (int i = tid; i < (int)(sizeof(SeqDev) / 4); i += kFxThreads) d_sq[i] = s_sq[i];
+        unsigned* d_fr = (unsigned*)(smem_raw + 2048);
+        const unsigned* s_fr0 = (const unsigned*)&blk->fr[0];
+        for (int i = tid; i < (int)(sizeof(FrameSc) * V2E_MAX_FRAMES / 4); i += kFxThreads) d_fr[i] = s_fr0[i];
+    }
+    __syncthreads();
+    const SeqDev& sq = *(const SeqDev*)(smem_raw + 3840);
     FxWork& fx = prm.fx[seq];
-    const int P = cfg.P, nb = cfg.nb, T = sq.T;
+    const int P = cfg.P, nb = SPEC ? kFxSpecNb : cfg.nb, T = SPEC ? kFxSpecT : sq.T;
     const bool leak = GENERIC ? (cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF) : (NOISE == 1);
     const bool shot = GENERIC ? (cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF) : (NOISE == 1);
     const bool philox = GENERIC ? (cfg.noise_mode == V2E_NOISE_PHILOX) : (NOISE == 1);
     const bool cutoff = GENERIC ? (cfg.cutoff_on != 0) : CUTOFF;
     const bool normalise = cfg.output_mode == V2E_OUT_VOXEL;
-    const int cap = prm.cap;
+    const int cap = SPEC ? fx_spec_cap(NOISE == 1) : prm.cap;
+    const int nw_off = SPEC ? FX_V0 + kFxSpecNb : prm.nw_off;
+    const int dl_off = SPEC ? FX_V0 + kFxSpecNb + kFxSpecT - 1 : prm.dl_off;
 
     // ---- shared memory carve-up ----------------------------------------------------------------
     float2* s_lut = (float2*)smem_raw;                                   // 2048
@@ -279,9 +542,11 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     unsigned* s_gmax = (unsigned*)(smem_raw + 3584);                     // 128: all tiles
     unsigned long long* s_acc = (unsigned long long*)(smem_raw + 3712);  // 5 * 8: tile partials
     unsigned long long* s_tot = (unsigned long long*)(smem_raw + 3752);  // 5 * 8: sequence totals
-    int* s_cnt = (int*)(smem_raw + 3792);                                // n_entries, n_spill, error
-    float* s_stat = (float*)(smem_raw + 3808);                           // mean, den, on
+    int* s_cnt = (int*)(smem_raw + 3792);   // 8: [0] entries, [1] spilled, [2] error, [5] task counter
+    float* s_stat = (float*)(smem_raw + 3824);                           // mean, den, on
     unsigned* s_ent = (unsigned*)(smem_raw + kFxHeader);
+    FxSmem sm;
+    sm.lut = s_lut; sm.fr = s_fr; sm.g = s_g; sm.max = s_max; sm.acc = s_acc;
 
     const int tile_px0 = tile * prm.tile_px;
     const int tile_n = max(0, min(prm.tile_px, P - tile_px0));
@@ -291,8 +556,9 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
 
     long long* tl = prm.timeline ? prm.timeline + (size_t)blockIdx.x * 32 : nullptr;
     FX_STAMP(0);
+    if (prm.timeline && blockIdx.x == 0 && tid == 0)
+        prm.timeline[160 * 32 + 2 * (fx.pad[0] & 127u)] = fx_now();
     load_lut(s_lut, cfg.lut);
-    if (tid < T) s_fr[tid] = prm.fr[seq][tid];
     if (tid < V2E_MAX_FRAMES) {
         // the guess: last pack's maxima (a hint kept in the workspace; any value is correct)
         const unsigned h = fx.guess[tid];
@@ -301,148 +567,182 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
         s_gmax[tid] = 0;
     }
     if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
-    if (tid < 3) s_cnt[tid] = 0;
+    if (tid < 8) s_cnt[tid] = 0;
     __syncthreads();
 
     FX_STAMP(1);
     // ================================ pass 1: stream ===============================================
+    // One pixel per lane, all frames of the pack in one go; the loads of the lane's next pixel are
+    // issued before the current one is computed.  Lanes past the end of the tile shadow its last
+    // pixel (the warp stays converged for the ballots) and write nothing.
     const bool compact_ok = T - 1 <= kFxChunk;
+    const float jit = cfg.leak_jitter;
+    struct FxIn {
+        float pos, neg, nra, base, lp, tm;
+        float x[kFxChunk];
+    };
+    auto load_in = [&](int l0, FxIn& in) {
+        const int p = tile_px0 + min(l0 + lane, tile_n - 1);
+        in.pos = __ldg(sq.pos + p);
+        in.neg = __ldg(sq.neg + p);
+        in.nra = leak ? __ldg(sq.nra + p) : 0.f;
+        if (sq.first_pack) {
+            in.base = load_frame1<FDT>(sq.frames, p);
+            in.lp = 0.f;
+            in.tm = 0.f;
+        } else {
+            in.base = sq.base[p];
+            in.lp = cutoff ? sq.lp[p] : 0.f;
+            in.tm = sq.tmem[p];
+        }
+#pragma unroll
+        for (int k = 0; k < kFxChunk; ++k)
+            in.x[k] = 1 + k < T ? load_frame1<FDT>(sq.frames, (long long)(1 + k) * P + p) : 0.f;
+    };
+    FxIn nxt;
+    if (warp * 32 < tile_n) load_in(warp * 32, nxt);
     for (int l0 = warp * 32; l0 < tile_n; l0 += kFxThreads) {
+        const FxIn in = nxt;
+        if (l0 + kFxThreads < tile_n) load_in(l0 + kFxThreads, nxt);
         const int l = l0 + lane;
         const bool valid = l < tile_n;
-        const int p = tile_px0 + (valid ? l : 0);
-        float base = 0.f, lp = 0.f, tm = 0.f, pos = 1.f, neg = 1.f, nlk = 0.f;
-        bool small = false;
+        const int p = tile_px0 + min(l, tile_n - 1);
+        const float pos = in.pos, neg = in.neg;
+        const float nlk = leak ? fmul(cfg.leak_rate, in.nra) : 0.f;
+        const float cmax = fmaxf(pos, neg);
+        const bool small = is_small_px(p, cfg.W);
+        // a frame value that is not an integer in 0..255 sends the pixel to the spill path
+        // (fp64 lin_log there); this loop then only ever indexes the table
+        bool bad = false;
+        float base, lp = 0.f, tm;
+        if (sq.first_pack) {
+            // _init (v2e_model.py:156-174,239-240)
+            const int v = __float2int_rn(in.base);
+            bad = !((float)v == in.base && (unsigned)v < 256u);
+            base = s_lut[v & 255].x;
+            lp = base;
+            tm = fadd(0.f, -sq.Tr);
+        } else {
+            base = in.base;
+            lp = in.lp;
+            tm = in.tm;
+            // pack rollover (v2e_model.py:329-330)
+            if (tm > 0.f) tm = fsub(tm, sq.bins_m1);
+            if (tm < 0.f) tm = -sq.Tr;
+        }
         int f = 0;
-        float sb = 0.f, slp = 0.f;
-        unsigned fb0 = 0, fb1 = 0, fb2 = 0;
-        bool allint = true;
-        if (valid) {
-            pos = __ldg(sq.pos + p);
-            neg = __ldg(sq.neg + p);
-            if (leak) nlk = fmul(cfg.leak_rate, __ldg(sq.nra + p));
-            small = is_small_px(p, cfg.W);
-            if (sq.first_pack) {
-                // _init (v2e_model.py:156-174,239-240)
-                float L0, I0;
-                log_inten(s_lut, load_frame1<FDT>(sq.frames, p), L0, I0);
-                base = L0;
-                lp = L0;
-                tm = fadd(0.f, -sq.Tr);
-            } else {
-                base = sq.base[p];
-                if (cutoff) lp = sq.lp[p];
-                tm = sq.tmem[p];
-                // pack rollover (v2e_model.py:329-330)
-                if (tm > 0.f) tm = fsub(tm, sq.bins_m1);
-                if (tm < 0.f) tm = -sq.Tr;
+        unsigned cm = 0;
+        float sb = 0.f;
+        float nwv[kFxChunk], dlv[kFxChunk];
+        const int nchunks = (T - 1 + kFxChunk - 1) / kFxChunk;
+        for (int c = 0; c < nchunks; ++c) {
+            const int n0 = 1 + c * kFxChunk;
+            float x[kFxChunk];
+#pragma unroll
+            for (int k = 0; k < kFxChunk; ++k) {
+                x[k] = in.x[k];
+                if (c > 0) x[k] = n0 + k < T ? load_frame1<FDT>(sq.frames, (long long)(n0 + k) * P + p) : 0.f;
             }
-            const int nchunks = (T - 1 + kFxChunk - 1) / kFxChunk;
-            for (int c = 0; c < nchunks; ++c) {
-                const int n0 = 1 + c * kFxChunk;
-                float x[kFxChunk];
+            uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+            if (philox) {
+                if (leak) wa = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 0);
+                if (shot || (leak && T - n0 > 8)) wb = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 1);
+            }
+            // (A) what the frames present to the pixel, whatever it does: straight-line code, the
+            // only chain across frames is the low-pass state (two dependent operations per frame)
+            float z0 = 0.f, z1 = 0.f;
+            cm = 0;
 #pragma unroll
-                for (int k = 0; k < kFxChunk; ++k)
-                    x[k] = n0 + k < T ? load_frame1<FDT>(sq.frames, (long long)(n0 + k) * P + p) : 0.f;
-                uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
-                if (philox) {
-                    if (leak) wa = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 0);
-                    if (shot || (leak && T - n0 > 8)) wb = noise_px<R>(sq.philox_ctr, (unsigned)p, (unsigned)c, 1);
+            for (int k = 0; k < kFxChunk; ++k) {
+                const int n = n0 + k;
+                nwv[k] = 0.f;
+                dlv[k] = 0.f;
+                if (n >= T) break;
+                const FrameSc& fs = s_fr[n];
+                const int v = __float2int_rn(x[k]);
+                bad = bad || !((float)v == x[k] && (unsigned)v < 256u);
+                const float2 li = s_lut[v & 255];
+                nwv[k] = li.x;
+                if (cutoff) {
+                    lp = lowpass(lp, li.x, li.y, small ? fs.s_small : fs.s_large);
+                    nwv[k] = lp;
                 }
-                float z0 = 0.f, z1 = 0.f;
+                if (leak) {
+                    float z;
+                    if (philox) {
+                        if ((k & 1) == 0) box_muller16(k < 8 ? (&wa.x)[k >> 1] : wb.w, z0, z1);
+                        z = (k & 1) ? z1 : z0;
+                    } else {
+                        z = __ldg(sq.leak_randn + (size_t)(n - 1) * P + p);
+                    }
+                    dlv[k] = leak_dec(nlk, jit, z, fs.sdt, pos);
+                    if (GENERIC && sq.dbg_leak_randn && philox && valid)
+                        sq.dbg_leak_randn[(size_t)(n - 1) * P + p] = z;
+                }
+                // may this frame hold a shot event?  Conservative first stage: the byte against
+                // the largest threshold either polarity could give (exact test in the resolve pass)
+                if (shot) {
+                    if (philox) {
+                        const unsigned byte = ((&wb.x)[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                        const float tmax = shot_thr256(fmaxf(fs.kp, fs.kn), cfg.shot_inten_m1, li.y, cmax);
+                        // second stage too (1 pixel-frame in ~256 gets here): the same uniform the
+                        // resolve pass will draw, against the same upper bound
+                        if ((float)byte < tmax &&
+                            shot_uniform<R>(sq.philox_ctr, n, p, byte) * 256.0f < tmax)
+                            cm |= 1u << k;
+                    } else {
+                        cm |= 1u << k;
+                    }
+                }
+            }
+            // (B) the memorised brightness up to the first frame that crosses a threshold
 #pragma unroll
-                for (int k = 0; k < kFxChunk; ++k) {
-                    const int n = n0 + k;
-                    if (n >= T) break;
-                    const FrameSc& fs = s_fr[n];
-                    const int v = __float2int_rn(x[k]);
-                    const bool isint = (float)v == x[k] && (unsigned)v < 256u;
-                    float2 li;
-                    if (__builtin_expect(isint, 1)) li = s_lut[v];
-                    else li = log_inten_slow(x[k]);
-                    allint = allint && isint;
-                    if (c == 0) {
-                        const unsigned sh = (unsigned)(v & 0xff) << (8 * (k & 3));
-                        if (k < 4) fb0 |= sh;
-                        else if (k < 8) fb1 |= sh;
-                        else fb2 |= sh;
-                    }
-                    const float lp_old = lp;
-                    float nw = li.x;
-                    if (cutoff) {
-                        lp = lowpass(lp, li.x, li.y, small ? fs.s_small : fs.s_large);
-                        nw = lp;
-                    }
-                    float z = 0.f;
-                    if (leak) {
-                        if (philox) {
-                            if ((k & 1) == 0) box_muller16(k < 8 ? (&wa.x)[k >> 1] : wb.w, z0, z1);
-                            z = (k & 1) ? z1 : z0;
-                        } else {
-                            z = __ldg(sq.leak_randn + (size_t)(n - 1) * P + p);
-                        }
-                    }
-                    if (!f) {
-                        const float b = leak ? leak_sub(base, nlk, cfg.leak_jitter, z, fs.sdt, pos) : base;
-                        const float diff = fsub(nw, b);
-                        const float ad = fabsf(diff);
-                        const bool live = ad > 1e-6f;
-                        const bool up = diff > 0.f;
-                        const float C = live ? (up ? pos : neg) : 0.f;
-                        bool maybe = live && ad >= fadd(C, 1e-9f);
-                        if (shot) {
-                            if (philox) {
-                                const float thr256 = shot_thr256(up ? fs.kp : fs.kn, cfg.shot_inten_m1, li.y, C);
-                                const unsigned byte = ((&wb.x)[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                                maybe = maybe || (float)byte < thr256;
-                            } else {
-                                maybe = maybe || live;
-                            }
-                        }
-                        if (maybe) {
-                            f = n;
-                            sb = base;
-                            slp = lp_old;
-                        } else {
-                            base = b;
-                            if (GENERIC) {
-                                const size_t o = (size_t)(n - 1) * P + p;
-                                if (sq.dbg_pol) sq.dbg_pol[o] = live ? (up ? 1 : -1) : 0;
-                                if (sq.dbg_cnt) sq.dbg_cnt[o] = 0;
-                                if (sq.dbg_final) sq.dbg_final[o] = 0;
-                                if (sq.dbg_leak_randn && leak && philox) sq.dbg_leak_randn[o] = z;
-                            }
-                        }
-                    }
+            for (int k = 0; k < kFxChunk; ++k) {
+                const int n = n0 + k;
+                if (n >= T) break;
+                const float b = leak ? fsub(base, dlv[k]) : base;
+                const float diff = fsub(nwv[k], b);
+                const float ad = fabsf(diff);
+                const bool live = ad > 1e-6f;
+                const bool up = diff > 0.f;
+                const float C = live ? (up ? pos : neg) : 0.f;
+                const float den = fadd(C, 1e-9f);
+                const bool hit = !f && valid && live && (ad >= den || ((cm >> k) & 1u));
+                if (hit) {
+                    f = n;
+                    sb = base;
+                }
+                if (!f) {
+                    base = b;
+                    if (valid) fx_dbg<GENERIC>(sq, P, n, p, live ? (up ? 1.f : -1.f) : 0.f, 0, 0);
                 }
             }
         }
-        // ---- classify: quiet -> finished; active -> compact entry or spill -------------------------
-        const bool active = valid && f != 0;
-        const bool want_compact = active && compact_ok && allint;
-        const unsigned cm = __ballot_sync(0xffffffffu, want_compact);
+        // ---- quiet -> finished; active -> compact entry or spill ------------------------------------
         int slot = -1;
-        if (cm) {
+        const bool want = f != 0 && compact_ok && !bad;
+        const unsigned am = __ballot_sync(0xffffffffu, want);
+        if (am) {
             int s0 = 0;
-            if (lane == 0) s0 = atomicAdd(&s_cnt[0], __popc(cm));
+            if (lane == 0) s0 = atomicAdd(&s_cnt[0], __popc(am));
             s0 = __shfl_sync(0xffffffffu, s0, 0);
-            if (want_compact) {
-                slot = s0 + __popc(cm & ((1u << lane) - 1u));
+            if (want) {
+                slot = s0 + __popc(am & ((1u << lane) - 1u));
                 if (slot >= cap) slot = -1;
             }
         }
-        const bool spill = active && slot < 0;
-        const unsigned sm = __ballot_sync(0xffffffffu, spill);
-        if (sm) {
+        const bool spill = valid && (bad || (f != 0 && slot < 0));
+        const unsigned spm = __ballot_sync(0xffffffffu, spill);
+        if (spm) {
             int s0 = 0;
-            if (lane == 0) s0 = atomicAdd(&s_cnt[1], __popc(sm));
+            if (lane == 0) s0 = atomicAdd(&s_cnt[1], __popc(spm));
             s0 = __shfl_sync(0xffffffffu, s0, 0);
-            if (spill) spill_list[s0 + __popc(sm & ((1u << lane) - 1u))] = (unsigned)l;
+            if (spill) spill_list[s0 + __popc(spm & ((1u << lane) - 1u))] = (unsigned)l;
         }
         if (valid) {
             if (!spill) {
                 if (cutoff) sq.lp[p] = lp;   // no event ever touches the low-pass state
-                if (!active) {
+                if (!f) {
                     sq.base[p] = base;
                     sq.tmem[p] = tm;
                 }
@@ -450,15 +750,17 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
             for (int b = 0; b < nb; ++b) fx_store_vox(cfg, sq.voxel, (size_t)b * P + p, 0.f);
             if (slot >= 0) {
                 unsigned* e = s_ent + slot;
-                e[FX_META * cap] = (unsigned)f | (tm == 0.f ? 32u : 0u) | ((unsigned)l << 8);
+                e[FX_META * cap] = (unsigned)f | (tm == 0.f ? 32u : 0u) | (cm << 6);
+                e[FX_IDX * cap] = (unsigned)l;
                 e[FX_BASE * cap] = __float_as_uint(sb);
-                e[FX_LP * cap] = __float_as_uint(slp);
                 e[FX_POS * cap] = __float_as_uint(pos);
                 e[FX_NEG * cap] = __float_as_uint(neg);
-                e[FX_NLK * cap] = __float_as_uint(nlk);
-                e[FX_F0 * cap] = fb0;
-                e[FX_F1 * cap] = fb1;
-                e[FX_F2 * cap] = fb2;
+#pragma unroll
+                for (int k = 0; k < kFxChunk; ++k) {
+                    if (k >= T - 1) break;
+                    e[(nw_off + k) * cap] = __float_as_uint(nwv[k]);
+                    if (leak) e[(dl_off + k) * cap] = __float_as_uint(dlv[k]);
+                }
             }
         }
     }
@@ -466,136 +768,48 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     const int n_ent = min(s_cnt[0], cap);
     const int n_spill = s_cnt[1];
     FX_STAMP(2);
-    if (tl && tid == 0) { tl[28] = n_ent; tl[29] = n_spill; }
+    if (tl && tid == 0) { tl[28] = n_ent; tl[29] = n_spill; tl[26] = 0; }
 
     // ================================ resolve passes ================================================
     int pass = 0;
     bool converged = false;
     for (; pass < T + 2; ++pass) {
-        FxAcc acc;
-        acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
-        // compact entries: inputs and voxel accumulators in shared memory
-        for (int e0 = warp * 32; e0 < n_ent; e0 += kFxThreads) {
-            const int e = e0 + lane;
-            const bool on = e < n_ent;
-            unsigned* ep = s_ent + (on ? e : 0);
-            const unsigned meta = ep[FX_META * cap];
-            const int f = on ? (int)(meta & 31u) : V2E_MAX_FRAMES;
-            const int l = (int)(meta >> 8);
-            const int p = tile_px0 + l;
-            float base = __uint_as_float(ep[FX_BASE * cap]);
-            float lp = __uint_as_float(ep[FX_LP * cap]);
-            float tm = (meta & 32u) ? 0.f : -sq.Tr;
-            const float pos = __uint_as_float(ep[FX_POS * cap]);
-            const float neg = __uint_as_float(ep[FX_NEG * cap]);
-            const float nlk = __uint_as_float(ep[FX_NLK * cap]);
-            const unsigned fb0 = ep[FX_F0 * cap], fb1 = ep[FX_F1 * cap], fb2 = ep[FX_F2 * cap];
-            float* vp = (float*)(ep + FX_V0 * cap);
-            if (on)
-                for (int b = 0; b < nb; ++b) vp[b * cap] = 0.f;
-            const bool small = is_small_px(p, cfg.W);
-            fx_resolve<FDT, R, GENERIC>(
-                prm, sq, on, p, f, base, lp, tm, pos, neg, nlk, small, leak, shot, philox, cutoff,
-                s_fr, s_g, s_max, vp, cap, acc, [&](int n) {
-                    const int k = n - 1;
-                    const unsigned w = k < 4 ? fb0 : (k < 8 ? fb1 : fb2);
-                    return s_lut[(w >> (8 * (k & 3))) & 0xffu];
-                });
-            if (on) {
-                ep[FX_OB * cap] = __float_as_uint(base);
-                ep[FX_OT * cap] = __float_as_uint(tm);
-            }
-        }
-        // spilled entries: inputs re-read from global memory, results kept in the workspace
-        for (int e0 = warp * 32; e0 < n_spill; e0 += kFxThreads) {
-            const int e = e0 + lane;
-            const bool on = e < n_spill;
-            const int l = on ? (int)spill_list[e] : 0;
-            const int p = tile_px0 + l;
-            float base, lp = 0.f, tm;
-            const float pos = __ldg(sq.pos + p), neg = __ldg(sq.neg + p);
-            const float nlk = leak ? fmul(cfg.leak_rate, __ldg(sq.nra + p)) : 0.f;
-            if (sq.first_pack) {
-                float L0, I0;
-                log_inten(s_lut, load_frame1<FDT>(sq.frames, p), L0, I0);
-                base = L0;
-                lp = L0;
-                tm = fadd(0.f, -sq.Tr);
-            } else {
-                base = sq.base[p];
-                if (cutoff) lp = sq.lp[p];
-                tm = sq.tmem[p];
-                if (tm > 0.f) tm = fsub(tm, sq.bins_m1);
-                if (tm < 0.f) tm = -sq.Tr;
-            }
-            float* vp = spill_vox + p;
-            if (on)
-                for (int b = 0; b < nb; ++b) vp[(size_t)b * P] = 0.f;
-            const bool small = is_small_px(p, cfg.W);
-            fx_resolve<FDT, R, GENERIC>(
-                prm, sq, on, p, 1, base, lp, tm, pos, neg, nlk, small, leak, shot, philox, cutoff,
-                s_fr, s_g, s_max, vp, P, acc, [&](int n) {
-                    float L, I;
-                    log_inten(s_lut, load_frame1<FDT>(sq.frames, (long long)n * P + p), L, I);
-                    return make_float2(L, I);
-                });
-            if (on) {
-                spill_state[p] = base;
-                spill_state[(size_t)P + p] = lp;
-                spill_state[(size_t)2 * P + p] = tm;
-            }
-        }
-        // ---- tile partials -> shared memory (integer adds: order-free) ----------------------------
-        {
-            unsigned long long nnz = acc.nnz, nev = acc.nev, lo = acc.lo, hi = acc.hi;
-            long long s1 = acc.s1;
-            for (int o = 16; o > 0; o >>= 1) {
-                nnz += __shfl_xor_sync(0xffffffffu, nnz, o);
-                nev += __shfl_xor_sync(0xffffffffu, nev, o);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                const unsigned long long olo = __shfl_xor_sync(0xffffffffu, lo, o);
-                const unsigned long long ohi = __shfl_xor_sync(0xffffffffu, hi, o);
-                lo += olo;
-                hi += ohi + (lo < olo ? 1ull : 0ull);
-            }
-            if (lane == 0 && (nnz | nev)) {
-                atomicAdd(&s_acc[0], nnz);
-                atomicAdd(&s_acc[1], (unsigned long long)s1);
-                const unsigned long long old = atomicAdd(&s_acc[2], lo);
-                atomicAdd(&s_acc[3], hi + (old + lo < old ? 1ull : 0ull));
-                atomicAdd(&s_acc[4], nev);
-            }
-        }
+        fx_resolve_compact<FDT, R, NOISE, SPEC>(prm, sq, sm, s_ent, n_ent, &s_cnt[5],
+                                                              tile_px0, leak, shot, philox);
+        if (n_spill)
+            fx_resolve_spill<FDT, R, GENERIC, SPEC>(prm, sq, sm, spill_list, n_spill, tile_px0, spill_vox,
+                                              spill_state, leak, shot, philox, cutoff);
         __syncthreads();
         if (pass < 8) FX_STAMP(3 + 3 * pass);
         // ---- grid barrier of this sequence: publish (maxima, partials), gather everybody's --------
         unsigned* slots = &fx.slot[pass & 1][0][0];
-        if (warp == 0) {
+        if (tid == 0) {
             unsigned* my = slots + tile * 32;
-            unsigned w = 0;
-            if (lane < 16) w = min(s_max[2 * lane], 0xffffu) | (min(s_max[2 * lane + 1], 0xffffu) << 16);
-            else if (lane < 26) w = ((const unsigned*)s_acc)[lane - 16];
-            if (lane < 26) my[lane] = w;
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                fx_st_release(my + 31, (unsigned)pass + 1u);
-            }
+            unsigned w[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = min(s_max[2 * i], 0xffffu) | (min(s_max[2 * i + 1], 0xffffu) << 16);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) w[16 + i] = ((const unsigned*)s_acc)[i];
+            w[26] = w[27] = 0u;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) ((uint4*)my)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            fx_st_release(my + 31, (unsigned)pass + 1u);   // release: orders this thread's stores above
         }
         if (tid < ((prm.tiles_per_seq + 31) & ~31)) {
             const bool has = tid < prm.tiles_per_seq;
             const unsigned* sl = slots + (has ? tid : 0) * 32;
-            unsigned wv[26];
+            uint4 q4[7];
 #pragma unroll
-            for (int i = 0; i < 26; ++i) wv[i] = 0;
+            for (int i = 0; i < 7; ++i) q4[i] = make_uint4(0, 0, 0, 0);
             if (has) {
                 int spins = 0;
                 while (fx_ld_relaxed(sl + 31) != (unsigned)pass + 1u)
                     if (++spins > kFxSpin) { s_cnt[2] = 1; break; }
                 (void)fx_ld_acquire(sl + 31);
 #pragma unroll
-                for (int i = 0; i < 26; ++i) wv[i] = __ldcg(sl + i);
+                for (int i = 0; i < 7; ++i) q4[i] = __ldcg((const uint4*)sl + i);
             }
+            const unsigned* wv = (const unsigned*)q4;
             const int nw = (T + 1) / 2;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -638,6 +852,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
             s_gmax[tid] = 0;
         }
         if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
+        if (tid == 0) s_cnt[5] = 0;
         __syncthreads();
     }
 
@@ -649,9 +864,9 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
         const double c = (double)s_tot[0];
         if (c > 0. && normalise) {
             // utils/event_process.py:166-175
-            const double a = (double)(long long)s_tot[1] * (1.0 / 8589934592.0);
+            const double a = (double)(long long)s_tot[1] * (1.0 / 2147483648.0);
             const double b = ((double)s_tot[3] * 18446744073709551616.0 + (double)s_tot[2]) *
-                             (1.0 / 8589934592.0) * (1.0 / 8589934592.0);
+                             (1.0 / 2147483648.0) * (1.0 / 2147483648.0);
             mean = fdiv((float)a, (float)c);
             den = fadd(sqrtf(fsub(fdiv((float)b, (float)c), fmul(mean, mean))), 1e-8f);
             on = 1.f;
@@ -674,15 +889,17 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     {
         const float mean = s_stat[0], den = s_stat[1];
         const bool norm = s_stat[2] != 0.f;
-        for (int e = tid; e < n_ent; e += kFxThreads) {
-            const unsigned* ep = s_ent + e;
-            const int p = tile_px0 + (int)(ep[FX_META * cap] >> 8);
+        for (int i = tid; i < n_ent; i += kFxThreads) {
+            const unsigned* ep = s_ent + i;
+            const int p = tile_px0 + (int)ep[FX_IDX * cap];
             sq.base[p] = __uint_as_float(ep[FX_OB * cap]);
             sq.tmem[p] = __uint_as_float(ep[FX_OT * cap]);
             for (int b = 0; b < nb; ++b) {
                 float v = __uint_as_float(ep[(FX_V0 + b) * cap]);
-                if (norm) v = fdiv(fmul(v != 0.f ? 1.f : 0.f, fsub(v, mean)), den);
-                fx_store_vox(cfg, sq.voxel, (size_t)b * P + p, v);
+                if (v != 0.f || !norm) {
+                    if (norm) v = fdiv(fsub(v, mean), den);   // nz * (v - mean) / (std + 1e-8)
+                    fx_store_vox(cfg, sq.voxel, (size_t)b * P + p, v);
+                }
             }
         }
         for (int e = tid; e < n_spill; e += kFxThreads) {
@@ -711,14 +928,18 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
         if (tid == 0) {
             __threadfence();
             fx.exit_count = 0;
+            if (prm.timeline && seq == 0) {
+                prm.timeline[160 * 32 + 2 * (fx.pad[0] & 127u) + 1] = fx_now();
+                fx.pad[0] += 1;
+            }
         }
     }
 }
 
 // ---- host side -----------------------------------------------------------------------------------
 struct FxPlan {
-    int ok;
-    int tiles_per_seq, tile_px, cap;
+    int ok, spec;
+    int tiles_per_seq, tile_px, cap, nw_off, dl_off;
     size_t smem;
 };
 
@@ -740,7 +961,7 @@ static int fx_device_props() {
     return V2E_OK;
 }
 
-static FxPlan fx_plan(const CfgDev& cfg, int n_seq) {
+static FxPlan fx_plan(const CfgDev& cfg, int n_seq, int T) {
     FxPlan pl{};
     if (fx_device_props() != V2E_OK || !g_fx_coop) return pl;
     if (cfg.output_mode == V2E_OUT_RAW) return pl;
@@ -751,11 +972,19 @@ static FxPlan fx_plan(const CfgDev& cfg, int n_seq) {
     tile_px = (tile_px + 31) & ~31;
     if (tile_px >= (1 << 24)) return pl;
     tiles = (cfg.P + tile_px - 1) / tile_px;
-    const int ewords = FX_V0 + cfg.nb;
+    const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
+    const int nfr = T - 1 < kFxChunk ? T - 1 : kFxChunk;
+    pl.nw_off = FX_V0 + cfg.nb;
+    pl.dl_off = pl.nw_off + nfr;
+    const int ewords = pl.dl_off + (leak ? nfr : 0);
     int cap = (int)(((size_t)g_fx_optin - kFxHeader) / (4u * ewords)) & ~31;
     if (cap > tile_px) cap = tile_px;
     if (cap < 32) return pl;
     pl.ok = 1;
+    // the specialised kernels assume the reference pack shape and the full B200 shared memory
+    // (their table may be larger than the tile: unused capacity)
+    pl.spec = T == kFxSpecT && cfg.nb == kFxSpecNb && g_fx_optin >= kFxSpecSmem;
+    if (pl.spec) cap = fx_spec_cap(leak);
     pl.tiles_per_seq = tiles;
     pl.tile_px = tile_px;
     pl.cap = cap;
@@ -767,13 +996,13 @@ int fixpoint_fits(const CfgDev& cfg, int frame_dtype, int n_seq) {
     (void)frame_dtype;
     const int rc = fx_device_props();
     if (rc != V2E_OK) return rc;
-    return fx_plan(cfg, n_seq).ok;
+    return fx_plan(cfg, n_seq, 10).ok;
 }
 
-template <int FDT, int R, int NOISE, bool CUTOFF>
-static int launch_fixpoint(const FxParams& prm, const FxPlan& pl, cudaStream_t st) {
+template <int FDT, int R, int NOISE, bool CUTOFF, bool SPEC>
+static int launch_fixpoint_v(const FxParams& prm, const FxPlan& pl, cudaStream_t st) {
     static bool attr_set = false;  // one process drives one device (multi-GPU)
-    auto kern = k_fixpoint<FDT, R, NOISE, CUTOFF>;
+    auto kern = k_fixpoint<FDT, R, NOISE, CUTOFF, SPEC>;
     int rc = V2E_OK;
     if (!attr_set) {
         rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -789,18 +1018,26 @@ static int launch_fixpoint(const FxParams& prm, const FxPlan& pl, cudaStream_t s
     return rc;
 }
 
+template <int FDT, int R, int NOISE, bool CUTOFF>
+static int launch_fixpoint(const FxParams& prm, const FxPlan& pl, cudaStream_t st) {
+    if (NOISE != 2 && pl.spec) return launch_fixpoint_v<FDT, R, NOISE, CUTOFF, NOISE != 2>(prm, pl, st);
+    return launch_fixpoint_v<FDT, R, NOISE, CUTOFF, false>(prm, pl, st);
+}
+
 template <int FDT>
 static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, int n_seq,
                           void* workspace, cudaStream_t st) {
-    const FxPlan pl = fx_plan(cfg, n_seq);
+    const FxPlan pl = fx_plan(cfg, n_seq, packs[0].sc.num_frames);
     if (!pl.ok) return V2E_ERR_UNSUPPORTED;
-    static thread_local FxParams prm;  // 16 KB: keep it off the stack
+    static thread_local FxParams prm;
     const StepLayout lay = step_layout(cfg, n_seq);
     prm.cfg = cfg;
     prm.n_seq = n_seq;
     prm.tiles_per_seq = pl.tiles_per_seq;
     prm.tile_px = pl.tile_px;
     prm.cap = pl.cap;
+    prm.nw_off = pl.nw_off;
+    prm.dl_off = pl.dl_off;
     prm.fx = (FxWork*)((char*)workspace + lay.fx_off);
     // the stepwise engine's accumulator areas are unused here: borrow them for the spilled pixels
     prm.spill_vox = (float*)((char*)workspace + lay.vox_off);
@@ -809,12 +1046,26 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     static const bool want_timeline = getenv("V2E_TIMELINE") != nullptr;
     prm.timeline = want_timeline ? (long long*)((char*)workspace + lay.tl_off) : nullptr;
     bool dbg = false;
+    static thread_local FxSeqBlock stage[V2E_MAX_SEQ_PER_LAUNCH];
+    static thread_local unsigned ring_pos = 0;
     for (int s = 0; s < n_seq; ++s) {
-        fill_seq(prm.seq[s], packs[s]);
+        FxSeqBlock& b = n_seq == 1 ? prm.one : stage[s];
+        fill_seq(b.sq, packs[s]);
         for (int n = 1; n < packs[s].sc.num_frames; ++n)
-            prm.fr[s][n] = make_frame_sc(cfg, packs[s].sc.fr[n]);
+            b.fr[n] = make_frame_sc(cfg, packs[s].sc.fr[n]);
         const v2e_pack& p = packs[s];
         dbg = dbg || p.dbg_pol || p.dbg_cnt || p.dbg_final || p.dbg_leak_randn || p.dbg_shot;
+    }
+    prm.blocks = nullptr;
+    if (n_seq > 1) {
+        // the records of a multi-sequence launch go through the workspace, copied in stream order
+        // (a ring of slots: the copy for launch i+1 never touches what launch i is reading)
+        FxSeqBlock* slot = (FxSeqBlock*)((char*)workspace + lay.fxblk_off) +
+                           (size_t)(ring_pos++ % kFxBlkRing) * V2E_MAX_SEQ_PER_LAUNCH;
+        const int rc = cuda_ok(cudaMemcpyAsync(slot, stage, sizeof(FxSeqBlock) * n_seq,
+                                               cudaMemcpyHostToDevice, st));
+        if (rc != V2E_OK) return rc;
+        prm.blocks = slot;
     }
     const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
     const bool shot = cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF;

@@ -23,6 +23,7 @@ Differences from the reference, all documented in DESIGN.md:
 """
 from __future__ import annotations
 
+import ctypes as C
 import logging
 import math
 import random
@@ -289,6 +290,10 @@ class EventEmulator(nn.Module):
 
     def check_status(self) -> None:
         """Raise if the last pack reported a contract violation (synchronises)."""
+        clip = getattr(self, "_clip_meta", None)
+        if clip is not None:
+            self._clip_meta = None
+            self._raise_on_status(int(clip[:, 2].max().item()))
         meta = getattr(self, "_last_meta", None)
         if meta is not None:
             self._raise_on_status(int(meta[2].item()))
@@ -301,6 +306,98 @@ class EventEmulator(nn.Module):
                 _cabi.ENGINE_PERSISTENT: "persistent",
                 _cabi.ENGINE_RUNAHEAD: "runahead",
                 _cabi.ENGINE_FIXPOINT: "fixpoint"}.get(self._launch.resolve_engine())
+
+    def forward_clip(self, frames, t_frames, events=None):
+        """Emulate K consecutive packs in one call (extension; voxel_grid output only).
+
+        Equivalent to ``[self(frames[k:k+1], t_frames[k]) for k in range(K)]`` (the loop
+        test.py:115-121 runs around the reference emulator), but the K launches are enqueued
+        back to back by one C call (`v2e_clip_forward`) with every host-side scalar prepared
+        ahead, so the device never waits for Python between packs.
+
+        frames: [K, T, H, W] on the CUDA device (float32 / uint8 / bfloat16), or a sequence of K
+        tensors [1, T, H, W] / [T, H, W] of one shape and dtype; t_frames: sequence of K stamp
+        tensors ([1,2] or [1,T]).  events: optional list of 2K torch.cuda.Event
+        (timing enabled) recorded before / after each pack's launch.
+        Returns (voxels [K, num_bins, H, W], num_events int64[K] on the device).  Nothing
+        synchronises; call ``check_status()`` at a convenient point.
+        """
+        if self.output_mode != "voxel_grid":
+            raise NotImplementedError("forward_clip serves output_mode='voxel_grid'")
+        if self.noise_mode == "injected" or self.debug_maps:
+            raise NotImplementedError("forward_clip: injected noise / debug maps go through forward()")
+        if isinstance(frames, torch.Tensor):
+            if frames.dim() != 4:
+                raise ValueError("frames must be [num_packs, num_frames, height, width]")
+            frames = list(frames.unbind(0))
+        flist = []
+        for fr in frames:
+            if not fr.is_cuda:
+                raise RuntimeError("frames must be on the CUDA device (no CPU fallback)")
+            if fr.dtype not in ops._FRAME_DT:
+                fr = fr.float()
+            fr = fr.contiguous()
+            flist.append(fr.reshape(fr.shape[-3:]))
+        if not flist or any(f.shape != flist[0].shape or f.dtype != flist[0].dtype for f in flist):
+            raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
+        frames = flist
+        K = len(frames)
+        num_frames, height, width = frames[0].shape
+        if len(t_frames) != K:
+            raise ValueError("need one stamp tensor per pack")
+        if not (2 <= num_frames <= _cabi.MAX_FRAMES):
+            raise ValueError(f"num_frames must be in [2,{_cabi.MAX_FRAMES}]")
+        dev = self._dev
+        first = self.base_log_frame is None
+        if first:
+            ext = getattr(self, "_planes_external", False)
+            keep = (self.pos_thres, self.neg_thres, self.noise_rate_array) if ext else None
+            self._init(height, width)
+            if ext:
+                self.pos_thres, self.neg_thres, self.noise_rate_array = keep
+        pl = self._get_launch(height, width, frames[0].dtype)
+        packs = (_cabi.Pack * K)()
+        out = torch.empty((K, self.num_bins, height, width), dtype=self.voxel_dtype, device=dev)
+        meta = torch.zeros((K, 4), dtype=torch.int32, device=dev)   # num_events (i64), status, pad
+        ostride = out.stride(0) * out.element_size()
+        for k in range(K):
+            pk = packs[k]
+            pack_scalars(t_frames[k], num_frames, self.num_bins, self._refractory_host,
+                         self.cutoff_hz, self.ql, self.qs, self.shot_noise_rate_hz,
+                         self._t_prev, first and k == 0, out=pk.sc)
+            pk.frames = frames[k].data_ptr()
+            pk.base_log_frame = self.base_log_frame.data_ptr()
+            pk.lp_log_frame0 = self.lp_log_frame0.data_ptr()
+            pk.timestamp_mem = self.timestamp_mem.data_ptr()
+            pk.pos_thres = self.pos_thres.data_ptr()
+            pk.neg_thres = self.neg_thres.data_ptr()
+            pk.noise_rate = ops._ptr(self.noise_rate_array)
+            pk.voxel = out.data_ptr() + k * ostride
+            pk.num_events = meta.data_ptr() + 16 * k
+            pk.status = meta.data_ptr() + 16 * k + 8
+            pk.philox_seed = self.philox_seed
+            pk.philox_offset = self._pack_counter
+            self._pack_counter += 1
+        self.t_previous = self._t_prev.value
+        self.frame_counter += K * num_frames
+        evp = None
+        if events is not None:
+            if len(events) != 2 * K:
+                raise ValueError("need 2 events per pack")
+            evp = (C.c_void_p * (2 * K))()
+            for i, e in enumerate(events):
+                e.record()                      # forces creation of the cudaEvent_t
+                evp[i] = e.cuda_event
+        rc = pl._lib.v2e_clip_forward(C.byref(pl.cfg), packs, K, self._workspace.data_ptr(),
+                                      self._workspace.numel(),
+                                      torch.cuda.current_stream(dev).cuda_stream, evp)
+        _cabi.check(rc, "v2e_clip_forward")
+        self._clip_keep = (frames, packs)       # keep the inputs alive until the stream is done
+        self._last_meta = meta[-1]
+        self._clip_meta = meta
+        num_events = meta[:, 0:2].contiguous().view(torch.int64).reshape(K)
+        self.num_events = num_events
+        return out, num_events
 
     def forward(self, frames, t_frames):
         """Compute events based on a sequence of frames (v2e_model.py:290-536).
