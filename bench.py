@@ -8,12 +8,14 @@ fused emulate+voxelize+normalise path.  Metric: Gpixel-frames/s = sequences*H*W*
 summed over ranks (weak scaling: each rank owns its own sequences; no collective on the data
 path).  One JSON line is printed by rank 0.
 
-  value     device-resident inputs (a ring of distinct packs larger than L2), timed with CUDA
+  value     device-resident inputs (a ring of distinct packs larger than L2), enqueued in
+            clips of 50 packs (EventEmulator.forward_clip -> v2e_clip_forward), timed with CUDA
             events, barrier + synchronize on both sides, max over ranks.
   e2e       same metric through the public EventEmulator.forward with frames in pinned HOST
             memory: per step one H2D copy of the pack and a D2H read of num_events.
   roofline  algorithmic bytes (92 B/pixel/pack) / mean kernel duration (CUDA
-            events around each launch) vs MEASURED_PEAKS.json hbm_gbs.
+            events around each launch, over a region of up to 200 launches that follows the
+            timed one: the events themselves cost ~20 us per launch) vs MEASURED_PEAKS.json.
   cpu_baseline  the CPU oracle port (oracle/v2e_oracle.c, OpenMP) on a bounded sample.
 
 --impl reference times the CPU port on the host cores (the reference itself is pure Python and
@@ -49,7 +51,9 @@ EMU = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, s
            pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)     # cfg2 params + model_v2e2v.py:56-57
 ALGO_BYTES_PER_PIXEL_PACK = 92      # 9 f32 frames + 5 f32 bins + 6 planes in + 3 planes out
 # measured DRAM bytes per launch (ncu --set full, profiles/r01_*): (workload, noise, engine)
-TRAFFIC_BYTES = {("cfg3", "philox", "persistent"): 55447040 + 3553024}
+TRAFFIC_BYTES = {("cfg3", "philox", "persistent"): 55447040 + 3553024,
+                 ("cfg3", "philox", "fixpoint"): 55576576 + 3887360,
+                 ("cfg3", "off", "fixpoint"): 51731968 + 3537152}
 
 
 def peaks():
@@ -67,6 +71,8 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):     # development aid
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -151,32 +157,57 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = lib.v2e_launch_count()
     # the K packs of a sequence are enqueued in clips (EventEmulator.forward_clip: one C call,
     # scalars prepared ahead), so the device does not wait for Python between launches
     CL = 50
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K * S)]
+
+    clip_ev = []
+
+    def run_clips(k_first, n_steps, events=None):
+        kk, i = k_first, 0
+        while kk < k_first + n_steps:
+            n = min(CL, k_first + n_steps - kk)
+            if events is None:      # one event per clip: where the time goes (stderr)
+                clip_ev.append((torch.cuda.Event(enable_timing=True), n, time.perf_counter()))
+                clip_ev[-1][0].record()
+            for s in range(S):
+                ems[s].forward_clip([packs[s][(kk + j) % ring] for j in range(n)],
+                                    [stamps(kk + j) for j in range(n)],
+                                    events=None if events is None else events[i:i + 2 * n])
+                i += 2 * n
+            kk += n
+        return kk
+
+    # warm the clip path too (its output block comes from cudaMalloc the first time: ~40 ms)
+    k = run_clips(k, CL)
+    clip_ev.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    launches0 = lib.v2e_launch_count()
     e0.record()
-    i = 0
-    k0 = k
-    while k < k0 + K:
-        n = min(CL, k0 + K - k)
-        for s in range(S):
-            ems[s].forward_clip([packs[s][(k + j) % ring] for j in range(n)],
-                                [stamps(k + j) for j in range(n)], events=ev[i:i + 2 * n])
-            i += 2 * n
-        k += n
+    k = run_clips(k, K)
     e1.record()
     barrier()
     for em in ems:
         em.check_status()
+    if rank == 0 and len(clip_ev) > 1:
+        per = [clip_ev[j][0].elapsed_time(clip_ev[j + 1][0]) / clip_ev[j][1] * 1e3
+               for j in range(len(clip_ev) - 1)]
+        host = [(clip_ev[j + 1][2] - clip_ev[j][2]) / clip_ev[j][1] * 1e6
+                for j in range(len(clip_ev) - 1)]
+        print("per-clip device us/step:", " ".join(f"{x:.0f}" for x in per), file=sys.stderr)
+        print("per-clip host   us/step:", " ".join(f"{x:.0f}" for x in host), file=sys.stderr)
     launches = lib.v2e_launch_count() - launches0
     ms_total = reduce_max(e0.elapsed_time(e1))
-    clocks = sampler.stop()
-    kern_ms = sorted(ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(K * S))
+    # kernel durations for the roofline: the same launches again, each bracketed by CUDA events
+    # on the launching stream (the events cost ~20 us per launch, so they stay out of `value`)
+    KR = min(K, 200)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * KR * S)]
+    k = run_clips(k, KR, events=ev)
+    barrier()
+    kern_ms = sorted(ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(KR * S))
     kern_mean_ms = sum(kern_ms) / len(kern_ms)
+    clocks = sampler.stop()     # sampled over the timed region and the kernel-timing region
     pxf_step = S * H * W * T_FRAMES
     value = world * pxf_step * K / (ms_total * 1e-3) / 1e9
 
@@ -259,7 +290,8 @@ def run_ours(args, rank, world, local_rank):
                                                               "k_phase_a/k_phase_b"),
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "kernel_ms_mean": round(kern_mean_ms, 5),
-                     "kernel_ms_min": round(kern_ms[0], 5)},
+                     "kernel_ms_min": round(kern_ms[0], 5),
+                     "kernel_launches_timed": KR * S},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -28,7 +28,7 @@ Tr = f32(f32(4 * 0.001) * f32(1 / 0.009))
 tfr = np.linspace(0, float(dur) * (T - 1), T).astype(f32)
 
 
-def run_pack(frames, base, lp, tmem, g):
+def run_pack(frames, base, lp, tmem, g, mask=None):
     """all pixels under guessed maxima g[n]; returns new state + produced maxima"""
     base, lp, tmem = base.copy(), lp.copy(), tmem.copy()
     m = np.zeros(T, np.int64)
@@ -42,7 +42,7 @@ def run_pack(frames, base, lp, tmem, g):
         pol = np.sign(diff).astype(f32)
         Cc = np.where(diff > 0, pos, np.where(diff < 0, neg, f32(0))).astype(f32)
         cnt = np.floor(np.abs(diff) / (Cc + f32(1e-9))).astype(np.int64)
-        m[n] = cnt.max()
+        m[n] = cnt.max() if mask is None else (cnt[mask].max() if mask.any() else 0)
         mx = int(g[n])
         ni = max(mx, 1)
         step = f32(f32(1) / f32(ni)) * dur
@@ -76,6 +76,23 @@ for k in range(int(sys.argv[3]) if len(sys.argv) > 3 else 6):
     else:
         tmem = np.where(tmem > 0, tmem - f32(NB - 1), tmem).astype(f32)
         tmem = np.where(tmem < 0, -Tr, tmem).astype(f32)
+    # hot pixels: first crossing is at least 4 thresholds (known without any guess)
+    _, _, _, _ = 0, 0, 0, 0
+    # hot pixels: some frame is at least theta thresholds away from the memorised brightness the
+    # pack starts with (an upper bound of every event count the pixel can reach: known without g)
+    theta = max(2, int(guess[1:].min()) // 2)
+    hot = np.zeros(P, bool)
+    l0 = lp.copy()
+    for n in range(1, T):
+        x = fr[n]; L, I = LOG[x], INT[x]
+        eps = np.minimum(np.where(small, f32(1), I * s_l), f32(1)).astype(f32)
+        l0 = ((f32(1) - eps) * l0 + eps * L).astype(f32)
+        d = np.abs(l0 - base); Cc = np.where(l0 > base, pos, neg)
+        hot |= d >= theta * Cc
+    _, _, _, mh = run_pack(fr, base, lp, tmem, guess, mask=hot)
+    gh = np.where(mh > 0, mh, guess)
+    _, _, _, mfull = run_pack(fr, base, lp, tmem, gh)
+    print(f"   hot pixels {hot.sum()} ({100*hot.mean():.2f}%): hot-only maxima {mh[1:].tolist()} -> full pass under them consistent: {(mfull[1:] == gh[1:]).all()}")
     g = guess.copy(); hist = []
     for it in range(12):
         b2, l2, t2, m = run_pack(fr, base, lp, tmem, g)

@@ -225,6 +225,39 @@ def test_forward_clip_equals_pack_loop(fdt):
     np.testing.assert_array_equal(a[3], b[3])
 
 
+@pytest.mark.parametrize("engine", ["auto", "persistent", "stepwise"])
+def test_batch_of_sequences_equals_one_by_one(engine):
+    """EventEmulatorBatch (S sequences per launch, BASELINE configs[3] geometry) == S separate
+    emulators: per-sequence barriers / maxima / statistics never mix sequences."""
+    from v2e2v_b200 import EventEmulator, EventEmulatorBatch
+    cfg, H, W, T, S, packs = gc.CFG2, 260, 346, 10, 5, 3
+    planes = [gc.make_planes(40 + s, H, W, cfg) for s in range(S)]
+    vids = [list(gc.video(60 + s, packs, T, H, W)) for s in range(S)]
+    batch = EventEmulatorBatch(S, device="cuda", noise_mode="philox", engine=engine, **cfg)
+    singles = []
+    for s in range(S):
+        batch[s].set_planes(*planes[s])
+        em = EventEmulator(device="cuda", noise_mode="philox", engine=engine, **cfg)
+        em.philox_seed = batch[s].philox_seed
+        em.set_planes(*planes[s])
+        singles.append(em)
+    for k in range(packs):
+        fr = torch.cat([vids[s][k][1] for s in range(S)]).cuda()
+        tf = torch.cat([vids[s][k][2] for s in range(S)])
+        vox, nev = batch(fr, tf)
+        batch.check_status()
+        for s in range(S):
+            v1, n1 = singles[s](vids[s][k][1].cuda(), vids[s][k][2])
+            assert int(nev[s].item()) == n1, (k, s)
+            np.testing.assert_array_equal(batch[s].base_log_frame.cpu().numpy(),
+                                          singles[s].base_log_frame.cpu().numpy())
+            np.testing.assert_array_equal(batch[s].timestamp_mem.cpu().numpy(),
+                                          singles[s].timestamp_mem.cpu().numpy())
+            np.testing.assert_allclose(vox[s].cpu().numpy(), v1[0].cpu().numpy(),
+                                       rtol=VOX_RTOL, atol=VOX_ATOL)
+    assert batch.resolved_engine == ("fixpoint" if engine == "auto" else engine)
+
+
 def test_time_order_error_and_reset():
     em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
     fr = torch.randint(0, 255, (1, 4, 16, 16)).float().cuda()

@@ -381,9 +381,9 @@ static __device__ __noinline__ void fx_resolve_spill(const FxParams& prm, const 
 // quotient; the event code behind it is reached by the lanes that cross (about one in eight).
 template <int FDT, int R, int NOISE, bool SPEC>
 static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, const SeqDev& sq,
-                                                       FxSmem sm, unsigned* s_ent, int n_ent,
-                                                       int* task_ctr, int tile_px0, bool leak_rt,
-                                                       bool shot_rt, bool philox_rt) {
+                                                       FxSmem sm, unsigned* s_ent, int n_cold,
+                                                       int n_hot, int* task_ctr, int tile_px0,
+                                                       bool leak_rt, bool shot_rt, bool philox_rt) {
     constexpr bool GENERIC = NOISE == 2;
     constexpr bool LEAKC = NOISE == 1;
     const bool leak = GENERIC ? leak_rt : (NOISE == 1);
@@ -398,14 +398,23 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
     const float Tr = sq.Tr;
     FxAcc acc;
     acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
-    const int ntasks = (n_ent + 31) >> 5;
+    // tasks of 32 entries, drawn from a queue: the hot entries (top of the table) first
+    const int th = (n_hot + 31) >> 5, tc = (n_cold + 31) >> 5;
     while (true) {
         int t = 0;
         if (lane == 0) t = atomicAdd(task_ctr, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= ntasks) break;
-        const int e = t * 32 + lane;
-        const bool on = e < n_ent;
+        if (t >= th + tc) break;
+        int e;
+        bool on;
+        if (t < th) {
+            const int i = t * 32 + lane;
+            on = i < n_hot;
+            e = cap - 1 - i;
+        } else {
+            e = (t - th) * 32 + lane;
+            on = e < n_cold;
+        }
         unsigned* ep = s_ent + (on ? e : 0);
         const unsigned meta = ep[FX_META * cap];
         const int p = tile_px0 + (int)ep[FX_IDX * cap];
@@ -437,8 +446,7 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
             const bool cross = live && ad >= den;
             if (act) base = b;
             const int cnt = cross ? (int)floorf(fdiv(ad, den)) : 0;   // :404
-            const int wm = __reduce_max_sync(0xffffffffu, cnt);
-            if (lane == 0 && (unsigned)wm > sm.max[n]) atomicMax(&sm.max[n], (unsigned)wm);
+            if ((unsigned)cnt > sm.max[n]) atomicMax(&sm.max[n], (unsigned)cnt);
             const bool bit = shot && live && ((cm >> (n - 1)) & 1u);
             const float pol = live ? (up ? 1.f : -1.f) : 0.f;
             int fin = 0;
@@ -569,6 +577,13 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
     if (tid < 8) s_cnt[tid] = 0;
     __syncthreads();
+    if (tid == 0) {
+        int gmin = 0x7fffffff;
+        for (int n = 1; n < T; ++n) gmin = min(gmin, s_g[n].mx);
+        s_stat[3] = (float)max(2, gmin / 2);   // theta of the "hot" test
+    }
+    __syncthreads();
+    const float theta = s_stat[3];
 
     FX_STAMP(1);
     // ================================ pass 1: stream ===============================================
@@ -633,6 +648,8 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
         int f = 0;
         unsigned cm = 0;
         float sb = 0.f;
+        bool hot = false;
+        const float base0 = base;
         float nwv[kFxChunk], dlv[kFxChunk];
         const int nchunks = (T - 1 + kFxChunk - 1) / kFxChunk;
         for (int c = 0; c < nchunks; ++c) {
@@ -712,6 +729,11 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
                     f = n;
                     sb = base;
                 }
+                // "hot": some frame is theta thresholds away from the brightness the pack starts
+                // with - a bound no event count of the pixel exceeds by much.  Scheduling hint:
+                // the hot entries alone usually decide the per-frame maxima (pre-pass below).
+                const float d0 = fsub(nwv[k], base0);
+                hot = hot || fabsf(d0) >= theta * (d0 > 0.f ? pos : neg);
                 if (!f) {
                     base = b;
                     if (valid) fx_dbg<GENERIC>(sq, P, n, p, live ? (up ? 1.f : -1.f) : 0.f, 0, 0);
@@ -719,16 +741,27 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
             }
         }
         // ---- quiet -> finished; active -> compact entry or spill ------------------------------------
+        // cold entries fill the table from the bottom, hot ones from the top
         int slot = -1;
         const bool want = f != 0 && compact_ok && !bad;
         const unsigned am = __ballot_sync(0xffffffffu, want);
         if (am) {
-            int s0 = 0;
-            if (lane == 0) s0 = atomicAdd(&s_cnt[0], __popc(am));
+            const unsigned hm = __ballot_sync(0xffffffffu, want && hot);
+            const unsigned lm = am & ~hm;
+            int s0 = 0, sl = 0, sh = 0;
+            if (lane == 0) {
+                s0 = atomicAdd(&s_cnt[0], __popc(am));
+                if (s0 + __popc(am) <= cap) {
+                    if (lm) sl = atomicAdd(&s_cnt[3], __popc(lm));
+                    if (hm) sh = atomicAdd(&s_cnt[4], __popc(hm));
+                }
+            }
             s0 = __shfl_sync(0xffffffffu, s0, 0);
-            if (want) {
-                slot = s0 + __popc(am & ((1u << lane) - 1u));
-                if (slot >= cap) slot = -1;
+            sl = __shfl_sync(0xffffffffu, sl, 0);
+            sh = __shfl_sync(0xffffffffu, sh, 0);
+            if (want && s0 + __popc(am) <= cap) {
+                const unsigned lt = (1u << lane) - 1u;
+                slot = hot ? cap - 1 - (sh + __popc(hm & lt)) : sl + __popc(lm & lt);
             }
         }
         const bool spill = valid && (bad || (f != 0 && slot < 0));
@@ -765,18 +798,22 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
         }
     }
     __syncthreads();
-    const int n_ent = min(s_cnt[0], cap);
+    const int n_cold = s_cnt[3], n_hot = s_cnt[4];
     const int n_spill = s_cnt[1];
     FX_STAMP(2);
-    if (tl && tid == 0) { tl[28] = n_ent; tl[29] = n_spill; tl[26] = 0; }
+    if (tl && tid == 0) { tl[28] = n_cold + n_hot; tl[29] = n_spill; tl[26] = n_hot; }
 
     // ================================ resolve passes ================================================
+    // round 0 is a pre-pass over the hot entries only: under last pack's guess it yields the
+    // maxima those entries reach, which are nearly always the image-wide ones - the guess of the
+    // first full pass.  Rounds >= 1 resolve every entry and test the guess they ran under.
     int pass = 0;
     bool converged = false;
-    for (; pass < T + 2; ++pass) {
-        fx_resolve_compact<FDT, R, NOISE, SPEC>(prm, sq, sm, s_ent, n_ent, &s_cnt[5],
-                                                              tile_px0, leak, shot, philox);
-        if (n_spill)
+    for (; pass < T + 3; ++pass) {
+        const bool pre = pass == 0;
+        fx_resolve_compact<FDT, R, NOISE, SPEC>(prm, sq, sm, s_ent, pre ? 0 : n_cold, n_hot,
+                                                &s_cnt[5], tile_px0, leak, shot, philox);
+        if (n_spill && !pre)
             fx_resolve_spill<FDT, R, GENERIC, SPEC>(prm, sq, sm, spill_list, n_spill, tile_px0, spill_vox,
                                               spill_state, leak, shot, philox, cutoff);
         __syncthreads();
@@ -845,9 +882,11 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
         if (pass < 8) FX_STAMP(4 + 3 * pass);
         // ---- m == g ? ------------------------------------------------------------------------------
         const int changed = __syncthreads_or(tid >= 1 && tid < T && (int)s_gmax[tid] != s_g[tid].mx);
-        if (!changed || s_cnt[2]) { converged = !changed; break; }
+        if (!pre && (!changed || s_cnt[2])) { converged = !changed; break; }
         if (tid < V2E_MAX_FRAMES) {
-            s_g[tid] = frame_globals((int)s_gmax[tid], sq.duration, sq.Tr);
+            // after the pre-pass a frame no hot entry fired in keeps last pack's guess
+            const int mx = (pre && s_gmax[tid] == 0) ? s_g[tid].mx : (int)s_gmax[tid];
+            s_g[tid] = frame_globals(mx, sq.duration, sq.Tr);
             s_max[tid] = 0;
             s_gmax[tid] = 0;
         }
@@ -857,7 +896,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     }
 
     FX_STAMP(27);
-    if (tl && tid == 0) tl[30] = pass + 1;
+    if (tl && tid == 0) tl[30] = pass + 1;   // rounds run, pre-pass included
     // ================================ commit =========================================================
     if (tid == 0) {
         float mean = 0.f, den = 1.f, on = 0.f;
@@ -889,8 +928,8 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     {
         const float mean = s_stat[0], den = s_stat[1];
         const bool norm = s_stat[2] != 0.f;
-        for (int i = tid; i < n_ent; i += kFxThreads) {
-            const unsigned* ep = s_ent + i;
+        for (int i = tid; i < n_cold + n_hot; i += kFxThreads) {
+            const unsigned* ep = s_ent + (i < n_cold ? i : cap - 1 - (i - n_cold));
             const int p = tile_px0 + (int)ep[FX_IDX * cap];
             sq.base[p] = __uint_as_float(ep[FX_OB * cap]);
             sq.tmem[p] = __uint_as_float(ep[FX_OT * cap]);

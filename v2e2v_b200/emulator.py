@@ -307,6 +307,35 @@ class EventEmulator(nn.Module):
                 _cabi.ENGINE_RUNAHEAD: "runahead",
                 _cabi.ENGINE_FIXPOINT: "fixpoint"}.get(self._launch.resolve_engine())
 
+    def _prep_pack(self, pk, fr, t_frames, vox_ptr, meta_ptr):
+        """Fill one v2e_pack (voxel output, no debug maps) for frames `fr` [T,H,W] and advance the
+        host-side state (time, pack counter).  meta_ptr: 16 zeroed bytes (num_events i64, status)."""
+        num_frames, height, width = fr.shape
+        first = self.base_log_frame is None
+        if first:
+            ext = getattr(self, "_planes_external", False)
+            keep = (self.pos_thres, self.neg_thres, self.noise_rate_array) if ext else None
+            self._init(height, width)
+            if ext:
+                self.pos_thres, self.neg_thres, self.noise_rate_array = keep
+        pack_scalars(t_frames, num_frames, self.num_bins, self._refractory_host, self.cutoff_hz,
+                     self.ql, self.qs, self.shot_noise_rate_hz, self._t_prev, first, out=pk.sc)
+        self.t_previous = self._t_prev.value
+        self.frame_counter += num_frames
+        pk.frames = fr.data_ptr()
+        pk.base_log_frame = self.base_log_frame.data_ptr()
+        pk.lp_log_frame0 = self.lp_log_frame0.data_ptr()
+        pk.timestamp_mem = self.timestamp_mem.data_ptr()
+        pk.pos_thres = self.pos_thres.data_ptr()
+        pk.neg_thres = self.neg_thres.data_ptr()
+        pk.noise_rate = ops._ptr(self.noise_rate_array)
+        pk.voxel = vox_ptr
+        pk.num_events = meta_ptr
+        pk.status = meta_ptr + 8
+        pk.philox_seed = self.philox_seed
+        pk.philox_offset = self._pack_counter
+        self._pack_counter += 1
+
     def forward_clip(self, frames, t_frames, events=None):
         """Emulate K consecutive packs in one call (extension; voxel_grid output only).
 
@@ -348,38 +377,14 @@ class EventEmulator(nn.Module):
         if not (2 <= num_frames <= _cabi.MAX_FRAMES):
             raise ValueError(f"num_frames must be in [2,{_cabi.MAX_FRAMES}]")
         dev = self._dev
-        first = self.base_log_frame is None
-        if first:
-            ext = getattr(self, "_planes_external", False)
-            keep = (self.pos_thres, self.neg_thres, self.noise_rate_array) if ext else None
-            self._init(height, width)
-            if ext:
-                self.pos_thres, self.neg_thres, self.noise_rate_array = keep
         pl = self._get_launch(height, width, frames[0].dtype)
         packs = (_cabi.Pack * K)()
         out = torch.empty((K, self.num_bins, height, width), dtype=self.voxel_dtype, device=dev)
         meta = torch.zeros((K, 4), dtype=torch.int32, device=dev)   # num_events (i64), status, pad
         ostride = out.stride(0) * out.element_size()
         for k in range(K):
-            pk = packs[k]
-            pack_scalars(t_frames[k], num_frames, self.num_bins, self._refractory_host,
-                         self.cutoff_hz, self.ql, self.qs, self.shot_noise_rate_hz,
-                         self._t_prev, first and k == 0, out=pk.sc)
-            pk.frames = frames[k].data_ptr()
-            pk.base_log_frame = self.base_log_frame.data_ptr()
-            pk.lp_log_frame0 = self.lp_log_frame0.data_ptr()
-            pk.timestamp_mem = self.timestamp_mem.data_ptr()
-            pk.pos_thres = self.pos_thres.data_ptr()
-            pk.neg_thres = self.neg_thres.data_ptr()
-            pk.noise_rate = ops._ptr(self.noise_rate_array)
-            pk.voxel = out.data_ptr() + k * ostride
-            pk.num_events = meta.data_ptr() + 16 * k
-            pk.status = meta.data_ptr() + 16 * k + 8
-            pk.philox_seed = self.philox_seed
-            pk.philox_offset = self._pack_counter
-            self._pack_counter += 1
-        self.t_previous = self._t_prev.value
-        self.frame_counter += K * num_frames
+            self._prep_pack(packs[k], frames[k], t_frames[k], out.data_ptr() + k * ostride,
+                            meta.data_ptr() + 16 * k)
         evp = None
         if events is not None:
             if len(events) != 2 * K:
@@ -518,3 +523,113 @@ class EventEmulator(nn.Module):
                 rows = rows[torch.argsort(key)]
             return rows, n
         return out, n
+
+
+class EventEmulatorBatch(nn.Module):
+    """S independent sequences emulated together (extension): one `EventEmulator` (batch size 1,
+    the only well-defined batch semantics of the reference, SURVEY.md trap T1) per sequence, but
+    up to 16 sequences share ONE launch of `v2e_pack_forward` (their CTAs are grouped per
+    sequence; barriers, maxima and normalisation statistics stay per sequence).  Results are
+    those of running the S emulators one after another.
+
+    forward(frames, t_frames): frames [S, T, H, W] (or a sequence of S tensors [1,T,H,W] /
+    [T,H,W]) on the CUDA device, t_frames [S, 2] / [S, T] (or a sequence of S [1,·] tensors).
+    Returns (voxels [S, num_bins, H, W], num_events int64[S] on the device); nothing
+    synchronises (call `check_status()`).  voxel_grid output, PHILOX / no noise only.
+    """
+
+    MAX_PER_LAUNCH = _cabi.MAX_SEQ_PER_LAUNCH
+
+    def __init__(self, n_sequences, output_mode="voxel_grid", **kwargs):
+        super().__init__()
+        if output_mode != "voxel_grid":
+            raise NotImplementedError("EventEmulatorBatch serves output_mode='voxel_grid'")
+        if n_sequences < 1:
+            raise ValueError("n_sequences must be >= 1")
+        self.emulators = nn.ModuleList([EventEmulator(output_mode, **kwargs)
+                                        for _ in range(n_sequences)])
+        for i, em in enumerate(self.emulators):
+            if em.noise_mode == "injected" or em.debug_maps:
+                raise NotImplementedError("injected noise / debug maps: use EventEmulator")
+            # one Philox key per sequence (the stream is indexed by pixel and pack only)
+            em.philox_seed = (em.philox_seed + i * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        self._groups = None
+        self._key = None
+        self._meta = None
+
+    def __len__(self):
+        return len(self.emulators)
+
+    def __getitem__(self, i):
+        return self.emulators[i]
+
+    def reset(self, indices=None):
+        for i in (range(len(self.emulators)) if indices is None else indices):
+            self.emulators[i].reset()
+
+    def _get_groups(self, H, W, dtype):
+        key = (H, W, dtype)
+        if self._key != key:
+            S, g = len(self.emulators), self.MAX_PER_LAUNCH
+            self._groups = []
+            for a in range(0, S, g):
+                n = min(g, S - a)
+                pl = ops.PackLaunch(self.emulators[a]._config(H, W, dtype), n)
+                ws = torch.zeros(pl.workspace_bytes, dtype=torch.uint8,
+                                 device=self.emulators[a]._dev)
+                self._groups.append((a, n, pl, ws))
+            self._key = key
+        return self._groups
+
+    @property
+    def resolved_engine(self):
+        if not self._groups:
+            return None
+        return {_cabi.ENGINE_STEPWISE: "stepwise", _cabi.ENGINE_PERSISTENT: "persistent",
+                _cabi.ENGINE_RUNAHEAD: "runahead",
+                _cabi.ENGINE_FIXPOINT: "fixpoint"}.get(self._groups[0][2].resolve_engine())
+
+    def check_status(self):
+        if self._meta is not None:
+            meta, self._meta = self._meta, None
+            EventEmulator._raise_on_status(int(meta[:, 2].max().item()))
+
+    def forward(self, frames, t_frames):
+        S = len(self.emulators)
+        if isinstance(frames, torch.Tensor):
+            if frames.dim() != 4 or frames.size(0) != S:
+                raise ValueError("frames must be [n_sequences, num_frames, height, width]")
+            frames = list(frames.unbind(0))
+        if isinstance(t_frames, torch.Tensor):
+            t_frames = [t_frames[i:i + 1] for i in range(t_frames.size(0))]
+        if len(frames) != S or len(t_frames) != S:
+            raise ValueError("need one pack of frames and one stamp tensor per sequence")
+        flist = []
+        for fr in frames:
+            if not fr.is_cuda:
+                raise RuntimeError("frames must be on the CUDA device (no CPU fallback)")
+            if fr.dtype not in ops._FRAME_DT:
+                fr = fr.float()
+            fr = fr.contiguous()
+            flist.append(fr.reshape(fr.shape[-3:]))
+        if any(f.shape != flist[0].shape or f.dtype != flist[0].dtype for f in flist):
+            raise ValueError("all sequences of a batch share one frame shape and dtype")
+        T, H, W = flist[0].shape
+        if not (2 <= T <= _cabi.MAX_FRAMES):
+            raise ValueError(f"num_frames must be in [2,{_cabi.MAX_FRAMES}]")
+        em0 = self.emulators[0]
+        dev = em0._dev
+        out = torch.empty((S, em0.num_bins, H, W), dtype=em0.voxel_dtype, device=dev)
+        meta = torch.zeros((S, 4), dtype=torch.int32, device=dev)
+        ostride = out.stride(0) * out.element_size()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for a, n, pl, ws in self._get_groups(H, W, flist[0].dtype):
+            for j in range(n):
+                i = a + j
+                self.emulators[i]._prep_pack(pl.packs[j], flist[i], t_frames[i],
+                                             out.data_ptr() + i * ostride, meta.data_ptr() + 16 * i)
+            pl.launch(ws, stream)
+        self._keep = flist
+        self._meta = meta
+        num_events = meta[:, 0:2].contiguous().view(torch.int64).reshape(S)
+        return out, num_events
