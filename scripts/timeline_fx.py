@@ -27,9 +27,18 @@ for k, fr, tfr in gc.video(1, 5, T, H, W):
     # NOTE: %globaltimer ticks are ~1.31 ns on this pool (calibrated against CUDA events in
     # scripts/clip_probe.py): multiply the figures below by 1.31 for microseconds
     rows = [("start", 0), ("setup done", 1), ("pass1 done", 2)]
-    for ps in range(min(npass, 8)):
+    for ps in range(min(npass, 4)):
         rows += [(f"resolve{ps} done", 3 + 3 * ps), (f"barrier{ps} done", 4 + 3 * ps)]
     rows += [("loop exit", 27), ("commit done", 31)]
+    for ps in range(2):
+        b = 14 + 6 * ps
+        ok = tl[:, b] > 0
+        if ok.any():
+            x = tl[ok]
+            d = lambda i, j: (x[:, b + j] - x[:, b + i]) / 1e3
+            print(f"   round {ps} task 0 (one warp): setup {d(0,1).mean():.2f}  frame loop {d(1,2).mean():.2f} (max {d(1,2).max():.2f})  "
+                  f"stats {d(2,3).mean():.2f}  | all warps: last task end -> after flush {d(4,5).mean():.2f}; "
+                  f"task0 start -> last warp's end {((x[:,b+4]-x[:,b])/1e3).mean():.2f} units")
     for name, i in rows:
         x = us(tl[:, i])
         print(f"   {name:16s} min {x.min():8.1f}  mean {x.mean():8.1f}  max {x.max():8.1f} us")

@@ -197,6 +197,7 @@ struct FxSmem {
     FrameGlobals* g;
     unsigned* max;
     unsigned long long* acc;
+    long long* tl;   // development aid: timeline slots of this CTA for the current round (or null)
 };
 
 // tile partials -> shared memory (integer adds: order-free)
@@ -405,6 +406,8 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
         if (lane == 0) t = atomicAdd(task_ctr, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= th + tc) break;
+        const bool probe = sm.tl && t == 0 && lane == 0;
+        if (probe) sm.tl[0] = fx_now();
         int e;
         bool on;
         if (t < th) {
@@ -433,6 +436,7 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
                 if (b < nb) vp[b * cap] = 0.f;
             fx_dbg_clear_shot<GENERIC>(sq, P, p, f, T);
         }
+        if (probe) sm.tl[1] = fx_now();
 #pragma unroll 1
         for (int n = 1; n < T; ++n) {   // not unrolled: the loop body should stay in the L0 I-cache
             const bool act = n >= f;
@@ -455,29 +459,51 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
                 if (!bit && g.gate) {
                     // The common event frame, inline: gate on (v2e_model.py:469), no shot draw.
                     // Iteration j of [0,c) is accepted iff ts_j - timestamp_mem > Tr (:419,:470),
-                    // monotone in j: the next accepted one is the first j that passes.
+                    // monotone in j, so the next accepted one is the first j that passes:
+                    // j == 0, or pred(j) && !pred(j-1).  The usual outcomes (nothing / j = 0 /
+                    // the closed-form estimate) are evaluated side by side without branches;
+                    // anything else (estimate off, a second event in the frame) takes the loop.
                     const float t0 = sm.fr[n].t_bin_prev, step = g.ts_step;
                     const int c = min(cnt, g.mx);
-                    int i = 0;
-                    while (i < c) {
-                        if (!(fsub(fadd(t0, fmul(step, (float)c)), tm) > Tr)) break;   // none left
-                        int j = i;
-                        if (!(fsub(fadd(t0, fmul(step, (float)(i + 1))), tm) > Tr)) {
-                            j = (int)floorf((Tr + tm - t0) * __fdividef(1.0f, step)) - 1;   // estimate
-                            j = min(max(j, i + 1), c - 1);
-                            while (j < c - 1 && !(fsub(fadd(t0, fmul(step, (float)(j + 1))), tm) > Tr)) ++j;
-                            while (j > i + 1 && fsub(fadd(t0, fmul(step, (float)j)), tm) > Tr) --j;
-                        }
-                        const float ts = fadd(t0, fmul(step, (float)(j + 1)));
+                    auto ts_of = [&](int j) { return fadd(t0, fmul(step, (float)(j + 1))); };
+                    auto accept = [&](float ts) {
                         tm = ts;
                         fin += 1;
-                        i = j + 1;
                         // v2e_model.py:478-502
                         const float ti = floorf(ts);
                         const float d = fsub(ts, ti);
                         const int bb = (int)ti;
                         if (bb >= 0 && bb < nb) vp[bb * cap] = fadd(vp[bb * cap], fmul(pol, fsub(1.0f, d)));
                         if (bb >= 0 && bb + 1 < nb) vp[(bb + 1) * cap] = fadd(vp[(bb + 1) * cap], fmul(pol, d));
+                    };
+                    const float tc = ts_of(c - 1), t1 = ts_of(0);
+                    const bool any = c > 0 && fsub(tc, tm) > Tr;      // else none is accepted
+                    const bool p_first = fsub(t1, tm) > Tr;
+                    int je = (int)floorf((Tr + tm - t0) * __fdividef(1.0f, step)) - 1;   // estimate
+                    je = max(min(je, c - 1), 1);
+                    const float tje = ts_of(je);
+                    const bool ok_est = c >= 2 && fsub(tje, tm) > Tr && !(fsub(ts_of(je - 1), tm) > Tr);
+                    int i = 0;
+                    bool slow = any;
+                    if (any && (p_first || ok_est)) {
+                        const float ts = p_first ? t1 : tje;
+                        i = (p_first ? 0 : je) + 1;
+                        accept(ts);
+                        slow = i < c && fsub(tc, ts) > Tr;            // another one fits (rare)
+                    }
+                    if (slow) {
+                        while (i < c) {
+                            if (!(fsub(tc, tm) > Tr)) break;          // none left
+                            int j = i;
+                            if (!(fsub(ts_of(i), tm) > Tr)) {
+                                j = (int)floorf((Tr + tm - t0) * __fdividef(1.0f, step)) - 1;
+                                j = min(max(j, i + 1), c - 1);
+                                while (j < c - 1 && !(fsub(ts_of(j), tm) > Tr)) ++j;
+                                while (j > i + 1 && fsub(ts_of(j - 1), tm) > Tr) --j;
+                            }
+                            accept(ts_of(j));
+                            i = j + 1;
+                        }
                     }
                 } else {
                     const unsigned long long r = fx_event_frame<FDT, R, GENERIC>(
@@ -492,6 +518,7 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
             }
             if (act) fx_dbg<GENERIC>(sq, P, n, p, pol, cnt, fin);
         }
+        if (probe) sm.tl[2] = fx_now();
         if (on) {
             ep[FX_OB * cap] = __float_as_uint(base);
             ep[FX_OT * cap] = __float_as_uint(tm);
@@ -499,8 +526,11 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
             for (int b = 0; b < (SPEC ? kFxSpecNb : V2E_MAX_BINS); ++b)
                 if (b < nb) fx_stat(vp[b * cap], acc.nnz, acc.s1, acc.lo, acc.hi);
         }
+        if (probe) sm.tl[3] = fx_now();
     }
+    if (sm.tl && lane == 0) atomicMax((unsigned long long*)&sm.tl[4], (unsigned long long)fx_now());
     fx_flush(acc, sm.acc);
+    if (sm.tl && lane == 0) atomicMax((unsigned long long*)&sm.tl[5], (unsigned long long)fx_now());
 }
 
 __device__ __forceinline__ void fx_store_vox(const CfgDev& cfg, void* voxel, size_t o, float v) {
@@ -554,7 +584,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     float* s_stat = (float*)(smem_raw + 3824);                           // mean, den, on
     unsigned* s_ent = (unsigned*)(smem_raw + kFxHeader);
     FxSmem sm;
-    sm.lut = s_lut; sm.fr = s_fr; sm.g = s_g; sm.max = s_max; sm.acc = s_acc;
+    sm.lut = s_lut; sm.fr = s_fr; sm.g = s_g; sm.max = s_max; sm.acc = s_acc; sm.tl = nullptr;
 
     const int tile_px0 = tile * prm.tile_px;
     const int tile_n = max(0, min(prm.tile_px, P - tile_px0));
@@ -811,13 +841,15 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     bool converged = false;
     for (; pass < T + 3; ++pass) {
         const bool pre = pass == 0;
+        sm.tl = (tl && pass < 2) ? tl + 14 + 6 * pass : nullptr;
+        if (sm.tl && tid < 6) sm.tl[tid] = 0;
         fx_resolve_compact<FDT, R, NOISE, SPEC>(prm, sq, sm, s_ent, pre ? 0 : n_cold, n_hot,
                                                 &s_cnt[5], tile_px0, leak, shot, philox);
         if (n_spill && !pre)
             fx_resolve_spill<FDT, R, GENERIC, SPEC>(prm, sq, sm, spill_list, n_spill, tile_px0, spill_vox,
                                               spill_state, leak, shot, philox, cutoff);
         __syncthreads();
-        if (pass < 8) FX_STAMP(3 + 3 * pass);
+        if (pass < 4) FX_STAMP(3 + 3 * pass);
         // ---- grid barrier of this sequence: publish (maxima, partials), gather everybody's --------
         unsigned* slots = &fx.slot[pass & 1][0][0];
         if (tid == 0) {
@@ -879,7 +911,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
             }
         }
         __syncthreads();
-        if (pass < 8) FX_STAMP(4 + 3 * pass);
+        if (pass < 4) FX_STAMP(4 + 3 * pass);
         // ---- m == g ? ------------------------------------------------------------------------------
         const int changed = __syncthreads_or(tid >= 1 && tid < T && (int)s_gmax[tid] != s_g[tid].mx);
         if (!pre && (!changed || s_cnt[2])) { converged = !changed; break; }
