@@ -258,6 +258,31 @@ def test_batch_of_sequences_equals_one_by_one(engine):
     assert batch.resolved_engine == ("fixpoint" if engine == "auto" else engine)
 
 
+@pytest.mark.parametrize("T,nb,vdt", [(14, 5, torch.float32), (10, 3, torch.float32),
+                                      (7, 8, torch.float32), (10, 5, torch.bfloat16)])
+def test_fixpoint_other_pack_shapes(T, nb, vdt):
+    """Fixed-point engine outside its specialised shape: packs longer than one Philox block /
+    than the compact table serves (T = 14: every active pixel takes the spill path), other bin
+    counts, bf16 voxel output - against the oracle."""
+    cfg = dict(gc.CFG2, num_bins=nb, leak_rate_hz=0, shot_noise_rate_hz=0)
+    H, W = 48, 80
+    pos, neg, _ = gc.make_planes(31, H, W, cfg)
+    em = gc.cuda_emulator(cfg, "fixpoint", voxel_dtype=vdt)
+    orc = OracleEmulator(**cfg)
+    em.set_planes(pos, neg)
+    orc.set_planes(pos, neg)
+    for k, fr, tfr in gc.video(12, 3, T, H, W):
+        ev, nev = em(fr.cuda(), tfr)
+        ov, onev = orc.forward(fr.numpy(), tfr)
+        assert nev == onev, f"pack {k}"
+        gc.assert_state_equal(em, orc, True, f"pack {k}")
+        if vdt == torch.bfloat16:
+            np.testing.assert_allclose(ev.float().cpu().numpy(), ov, rtol=1e-2, atol=1e-2)
+        else:
+            np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+    assert em.resolved_engine == "fixpoint"
+
+
 def test_time_order_error_and_reset():
     em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
     fr = torch.randint(0, 255, (1, 4, 16, 16)).float().cuda()

@@ -47,7 +47,9 @@ namespace v2e {
 constexpr int kFxThreads = V2E_FX_THREADS;
 constexpr int kFxWarps = kFxThreads / 32;
 constexpr int kFxChunk = 10;        // frames per unrolled chunk = frames per Philox block
-constexpr int kFxHeader = 4096;     // LUT, frame tables, reduction scratch
+constexpr int kFxHeader = 10240;    // LUT, frame tables, reduction scratch, entry order, histogram
+constexpr int kFxPermOff = 4096;    // byte offset of the entry order (u16[kFxPermMax]) in the header
+constexpr int kFxPermMax = 2816;    // most entries a tile's table may hold; 512 B of histogram follow
 constexpr int kFxSpin = 1 << 25;    // barrier poll limit (a lost CTA must not hang the GPU)
 // Specialised variants (SPEC): the reference's pack shape (10 frames, 5 bins) with everything the
 // address arithmetic needs known at compile time, for the 227 KB of shared memory a B200 CTA gets.
@@ -103,6 +105,7 @@ __host__ __device__ constexpr int fx_spec_ewords(bool leak) {
 __host__ __device__ constexpr int fx_spec_cap(bool leak) {
     return ((kFxSpecSmem - kFxHeader) / (4 * fx_spec_ewords(leak))) & ~31;
 }
+static_assert(fx_spec_cap(false) <= kFxPermMax && fx_spec_cap(true) <= kFxPermMax, "entry order table");
 
 // ---- memory-ordering helpers ---------------------------------------------------------------------
 __device__ __forceinline__ void fx_st_release(unsigned* p, unsigned v) {
@@ -197,6 +200,7 @@ struct FxSmem {
     FrameGlobals* g;
     unsigned* max;
     unsigned long long* acc;
+    const unsigned short* perm;   // entries ordered by first active frame: cold list, then hot list
     long long* tl;   // development aid: timeline slots of this CTA for the current round (or null)
 };
 
@@ -383,7 +387,8 @@ static __device__ __noinline__ void fx_resolve_spill(const FxParams& prm, const 
 template <int FDT, int R, int NOISE, bool SPEC>
 static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, const SeqDev& sq,
                                                        FxSmem sm, unsigned* s_ent, int n_cold,
-                                                       int n_hot, int* task_ctr, int tile_px0,
+                                                       int n_hot, int hot_off, int* task_ctr,
+                                                       int tile_px0,
                                                        bool leak_rt, bool shot_rt, bool philox_rt) {
     constexpr bool GENERIC = NOISE == 2;
     constexpr bool LEAKC = NOISE == 1;
@@ -399,7 +404,9 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
     const float Tr = sq.Tr;
     FxAcc acc;
     acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
-    // tasks of 32 entries, drawn from a queue: the hot entries (top of the table) first
+    // tasks of 32 entries, drawn from a queue: the hot list first, each list in the order of the
+    // first active frame (sm.perm), so that a task only walks the frames its entries need and
+    // the long tasks are drawn first
     const int th = (n_hot + 31) >> 5, tc = (n_cold + 31) >> 5;
     while (true) {
         int t = 0;
@@ -413,10 +420,11 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
         if (t < th) {
             const int i = t * 32 + lane;
             on = i < n_hot;
-            e = cap - 1 - i;
+            e = sm.perm[hot_off + (on ? i : 0)];
         } else {
-            e = (t - th) * 32 + lane;
-            on = e < n_cold;
+            const int i = (t - th) * 32 + lane;
+            on = i < n_cold;
+            e = sm.perm[on ? i : 0];
         }
         unsigned* ep = s_ent + (on ? e : 0);
         const unsigned meta = ep[FX_META * cap];
@@ -437,8 +445,9 @@ static __device__ __noinline__ void fx_resolve_compact(const FxParams& prm, cons
             fx_dbg_clear_shot<GENERIC>(sq, P, p, f, T);
         }
         if (probe) sm.tl[1] = fx_now();
+        const int n_first = __reduce_min_sync(0xffffffffu, f);
 #pragma unroll 1
-        for (int n = 1; n < T; ++n) {   // not unrolled: the loop body should stay in the L0 I-cache
+        for (int n = n_first; n < T; ++n) {   // not unrolled: the loop body should stay in the L0 I-cache
             const bool act = n >= f;
             const float b = leak ? fsub(base, dlp[n * cap]) : base;
             const float diff = fsub(nwp[n * cap], b);
@@ -582,9 +591,12 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     unsigned long long* s_tot = (unsigned long long*)(smem_raw + 3752);  // 5 * 8: sequence totals
     int* s_cnt = (int*)(smem_raw + 3792);   // 8: [0] entries, [1] spilled, [2] error, [5] task counter
     float* s_stat = (float*)(smem_raw + 3824);                           // mean, den, on
+    unsigned short* s_perm = (unsigned short*)(smem_raw + kFxPermOff);
+    int* s_hist = (int*)(smem_raw + kFxPermOff + 2 * kFxPermMax);   // 2 x 64 ints
+    static_assert(kFxPermOff + 2 * kFxPermMax + 512 <= kFxHeader, "header layout");
     unsigned* s_ent = (unsigned*)(smem_raw + kFxHeader);
     FxSmem sm;
-    sm.lut = s_lut; sm.fr = s_fr; sm.g = s_g; sm.max = s_max; sm.acc = s_acc; sm.tl = nullptr;
+    sm.lut = s_lut; sm.fr = s_fr; sm.g = s_g; sm.max = s_max; sm.acc = s_acc; sm.perm = s_perm; sm.tl = nullptr;
 
     const int tile_px0 = tile * prm.tile_px;
     const int tile_n = max(0, min(prm.tile_px, P - tile_px0));
@@ -606,6 +618,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     }
     if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
     if (tid < 8) s_cnt[tid] = 0;
+    if (tid < 128) s_hist[tid] = 0;
     __syncthreads();
     if (tid == 0) {
         int gmin = 0x7fffffff;
@@ -812,6 +825,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
             }
             for (int b = 0; b < nb; ++b) fx_store_vox(cfg, sq.voxel, (size_t)b * P + p, 0.f);
             if (slot >= 0) {
+                atomicAdd(&s_hist[(hot ? 32 : 0) + f], 1);   // for the ordering by first frame
                 unsigned* e = s_ent + slot;
                 e[FX_META * cap] = (unsigned)f | (tm == 0.f ? 32u : 0u) | (cm << 6);
                 e[FX_IDX * cap] = (unsigned)l;
@@ -830,6 +844,23 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     __syncthreads();
     const int n_cold = s_cnt[3], n_hot = s_cnt[4];
     const int n_spill = s_cnt[1];
+    // ---- order the entries by first active frame (counting sort; order within a frame is free) ---
+    if (tid == 0) {
+        int o = 0;
+        for (int i = 0; i < 64; ++i) {   // cold frames 0..31, then hot frames 0..31
+            const int c = s_hist[i];
+            s_hist[64 + i] = o;
+            o += c;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n_cold + n_hot; i += kFxThreads) {
+        const bool h = i >= n_cold;
+        const int e = h ? cap - 1 - (i - n_cold) : i;
+        const int f = (int)(s_ent[FX_META * cap + e] & 31u);
+        s_perm[atomicAdd(&s_hist[64 + (h ? 32 : 0) + f], 1)] = (unsigned short)e;
+    }
+    __syncthreads();
     FX_STAMP(2);
     if (tl && tid == 0) { tl[28] = n_cold + n_hot; tl[29] = n_spill; tl[26] = n_hot; }
 
@@ -842,8 +873,11 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
     for (; pass < T + 3; ++pass) {
         const bool pre = pass == 0;
         sm.tl = (tl && pass < 2) ? tl + 14 + 6 * pass : nullptr;
-        if (sm.tl && tid < 6) sm.tl[tid] = 0;
-        fx_resolve_compact<FDT, R, NOISE, SPEC>(prm, sq, sm, s_ent, pre ? 0 : n_cold, n_hot,
+        if (sm.tl) {
+            if (tid < 6) sm.tl[tid] = 0;
+            __syncthreads();
+        }
+        fx_resolve_compact<FDT, R, NOISE, SPEC>(prm, sq, sm, s_ent, pre ? 0 : n_cold, n_hot, n_cold,
                                                 &s_cnt[5], tile_px0, leak, shot, philox);
         if (n_spill && !pre)
             fx_resolve_spill<FDT, R, GENERIC, SPEC>(prm, sq, sm, spill_list, n_spill, tile_px0, spill_vox,
@@ -872,6 +906,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint(const __grid_constan
             for (int i = 0; i < 7; ++i) q4[i] = make_uint4(0, 0, 0, 0);
             if (has) {
                 int spins = 0;
+                // plain spinning: a __nanosleep back-off here made the barrier ~2 us slower
                 while (fx_ld_relaxed(sl + 31) != (unsigned)pass + 1u)
                     if (++spins > kFxSpin) { s_cnt[2] = 1; break; }
                 (void)fx_ld_acquire(sl + 31);
@@ -1050,6 +1085,7 @@ static FxPlan fx_plan(const CfgDev& cfg, int n_seq, int T) {
     const int ewords = pl.dl_off + (leak ? nfr : 0);
     int cap = (int)(((size_t)g_fx_optin - kFxHeader) / (4u * ewords)) & ~31;
     if (cap > tile_px) cap = tile_px;
+    if (cap > kFxPermMax) cap = kFxPermMax;
     if (cap < 32) return pl;
     pl.ok = 1;
     // the specialised kernels assume the reference pack shape and the full B200 shared memory
