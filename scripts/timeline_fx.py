@@ -28,17 +28,14 @@ for k, fr, tfr in gc.video(1, 5, T, H, W):
     # scripts/clip_probe.py): multiply the figures below by 1.31 for microseconds
     rows = [("start", 0), ("setup done", 1), ("pass1 done", 2)]
     for ps in range(min(npass, 4)):
-        rows += [(f"resolve{ps} done", 3 + 3 * ps), (f"barrier{ps} done", 4 + 3 * ps)]
+        rows += [(f"resolve{ps} done", 3 + 3 * ps)] + ([(f"arrived{ps}", 5 + 3 * ps)] if ps < 3 else []) + [(f"barrier{ps} done", 4 + 3 * ps)]
     rows += [("loop exit", 27), ("commit done", 31)]
-    for ps in range(2):
-        b = 14 + 6 * ps
-        ok = tl[:, b] > 0
+    if os.environ.get("V2E_STAMPS"):
+        fr = tl[:, 14:24].astype(np.float64)
+        ok = (fr > 0).all(axis=1)
         if ok.any():
-            x = tl[ok]
-            d = lambda i, j: (x[:, b + j] - x[:, b + i]) / 1e3
-            print(f"   round {ps} task 0 (one warp): setup {d(0,1).mean():.2f}  frame loop {d(1,2).mean():.2f} (max {d(1,2).max():.2f})  "
-                  f"stats {d(2,3).mean():.2f}  | all warps: last task end -> after flush {d(4,5).mean():.2f}; "
-                  f"task0 start -> last warp's end {((x[:,b+4]-x[:,b])/1e3).mean():.2f} units")
+            d = np.diff(fr[ok], axis=1) / 1e3
+            print("   pre-pass task 0, per frame (us): " + " ".join(f"{x:.2f}" for x in d.mean(axis=0)) + f"   | slow-path calls/tile in the pre-pass: shot {(tl[:,24] & 0xffff).mean():.1f} more {((tl[:,24] >> 16) & 0xffff).mean():.1f} est {(tl[:,24] >> 32).mean():.1f}")
     for name, i in rows:
         x = us(tl[:, i])
         print(f"   {name:16s} min {x.min():8.1f}  mean {x.mean():8.1f}  max {x.max():8.1f} us")

@@ -17,10 +17,10 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libv2e2v_b200.so")
 BUILD = os.path.join(PKG, "_build")
 
-CU_SOURCES = ["v2e_api.cu", "v2e_stepwise.cu", "v2e_persistent.cu", "v2e_runahead.cu", "v2e_fixpoint.cu",
+CU_SOURCES = ["v2e_api.cu", "v2e_stepwise.cu", "v2e_persistent.cu", "v2e_runahead.cu", "v2e_fixpoint.cu", "v2e_fixpoint_spec.cu",
               "v2e_voxel.cu"]
 C_SOURCES = ["host_scalars.c"]
-HEADERS = ["v2e_device.cuh", "v2e_engine.cuh", os.path.join("..", "..", "include", "v2e2v_b200.h")]
+HEADERS = ["v2e_device.cuh", "v2e_engine.cuh", "v2e_fixpoint.cuh", os.path.join("..", "..", "include", "v2e2v_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -55,16 +55,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
     log = []
+    jobs = []
     for src in CU_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(BUILD, src + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            extra = os.environ.get("V2E_NVCC_EXTRA", "").split()   # development aid
-            r = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o],
-                               capture_output=True, text=True)
-            log.append(r.stderr)
-            if r.returncode != 0:
-                raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr}")
+            jobs.append((src, s, o))
+
+    def _compile(job):
+        src, s, o = job
+        extra = os.environ.get("V2E_NVCC_EXTRA", "").split()   # development aid
+        r = subprocess.run([_nvcc(), *NVCC_FLAGS, *extra, "-c", s, "-o", o],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr}")
+        return r.stderr
+
+    if jobs:   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            log.extend(ex.map(_compile, jobs))
     for src in C_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(BUILD, src + ".o")
         objs.append(o)

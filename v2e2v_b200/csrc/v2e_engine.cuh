@@ -32,15 +32,22 @@ struct SeqWork {
 };
 using StepWork = SeqWork;
 
-// Per-sequence work area of the fixed-point engine.  `slot` is zero on entry and on exit;
-// `guess` is a hint that survives from pack to pack (any content is correct, see v2e_fixpoint.cu).
+// Per-sequence work area of the fixed-point engine.  Everything but `guess` is zero on entry and
+// on exit; `guess` is a hint that survives from pack to pack (any content is correct, see
+// v2e_fixpoint.cu).
+constexpr int kFxMaxRounds = V2E_MAX_FRAMES + 4;   // resolve rounds of one launch (pre-pass included)
 struct FxWork {
-    // grid barrier records, double-buffered by pass parity: per tile 16 words of per-frame maxima
-    // (two u16 each), 10 words of statistics partials, word 31 = pass tag (0: not arrived)
-    unsigned slot[2][kRaMaxTiles][32];
+    // grid barrier: `arrive` counts the CTAs that reached a barrier in this launch (monotone:
+    // round r is complete at tiles * (r + 1)).  What a round publishes is accumulated into that
+    // round's own words with order-free integer atomics before the arrival: the per-frame maxima
+    // (max) and the statistics partials (nnz, sum, three 40-bit limbs of the sum of squares,
+    // events: adds that cannot overflow 64 bits).  The last CTA to leave zeroes what was used.
+    unsigned arrive;
     unsigned exit_count;
-    unsigned pad[3];
+    unsigned pad[2];
     unsigned guess[V2E_MAX_FRAMES];  // last pack's per-frame max event count + 1 (0: none yet)
+    unsigned gmax[kFxMaxRounds][V2E_MAX_FRAMES];
+    unsigned long long stat[kFxMaxRounds][8];
 };
 
 struct StepLayout {

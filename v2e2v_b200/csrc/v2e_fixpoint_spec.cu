@@ -1,0 +1,859 @@
+// v2e_fixpoint_spec.cu — the fixed-point engine specialised for the reference's pack shape
+// (num_pack_frames = 10, num_bins = 5: utils/configs.py:6,18) with the two noise wirings that are
+// served without debug maps: none, or PHILOX leak + shot (what V2E2VNet hard-wires,
+// model_v2e2v.py:56-57).  Same algorithm, entry table, noise streams and results as the generic
+// kernel in v2e_fixpoint.cu (speculate on the per-frame maxima, verify, repeat); what differs is
+// how the work is laid out on the SM:
+//
+//   pass 1   two pixels per lane, 64-bit loads and stores, every frame of the pack in registers;
+//            the frame loop is straight-line code that only decides "may anything happen at this
+//            pixel" (|diff| against the smaller threshold, a zero test on the packed shot fields).
+//            Quiet pixels (~85 %) are finished here.  The others get a table entry holding the
+//            inputs no event can change: per frame the low-passed log intensity and the leak
+//            decrement.
+//   post     one entry per lane over the compact table: first active frame, brightness before
+//            it, "hot" flag; counting sort by first active frame.
+//   resolve  one entry per lane, voxel accumulators in registers, table addresses bumped per
+//            frame; a pixel's usual event frame (one event at the frame's first time stamp,
+//            whose bin and weights are per-frame constants) is a dozen instructions; per-frame
+//            maxima via one warp reduction; anything unusual (shot candidates, gate off) goes
+//            through the generic out-of-line code.
+//   barrier  order-free integer atomics on the round's own words + one arrival counter.
+#include "v2e_fixpoint.cuh"
+
+namespace v2e {
+
+constexpr int kSpNF = kFxSpecT - 1;   // frames 1..9 of the pack carry events
+#ifndef V2E_SP_HOT_LANES
+#define V2E_SP_HOT_LANES 32
+#endif
+constexpr int kSpHotLanes = V2E_SP_HOT_LANES;   // entries per task of the hot list
+
+// Per-frame constants of the resolve loop, all derived from the frame's guessed maximum
+// (v2e_model.py:405-422,469): the time axis of the frame's iterations and what an event at the
+// first time stamp needs (:478-502) - its stamp, bin and bilinear weights are the same for every
+// pixel of the image.  Counts are kept as floats (small integers, exact): no conversions on the
+// per-pixel dependency chain.
+struct SpFrameEv {
+    float ts1, wl, wr, bbf;     // iteration 0: stamp, weights of bins bb and bb+1, bb as a float
+    float t0, step, rstep, mxf; // time_frames[n-1], ts_step, ~1/ts_step (estimates only), max count
+};
+
+template <int FDT>
+__device__ __forceinline__ float2 sp_load_frame2(const void* __restrict__ f, long long idx) {
+    // idx is even and the plane is 16 B aligned
+    if (FDT == V2E_DT_U8) {
+        const uchar2 v = __ldg((const uchar2*)((const unsigned char*)f + idx));
+        return make_float2((float)v.x, (float)v.y);
+    }
+    if (FDT == V2E_DT_BF16) {
+        const unsigned v = __ldg((const unsigned*)((const unsigned short*)f + idx));
+        return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+    }
+    return __ldg((const float2*)((const float*)f + idx));
+}
+
+// frame value -> table index.  Integer-valued 0..255 maps to itself; anything else (fraction,
+// out of range, NaN) is flagged and the pixel takes the fp64 path of the generic code.
+template <int FDT>
+__device__ __forceinline__ unsigned sp_index(float x, bool& bad) {
+    unsigned v = min(__float2uint_rn(x), 255u);
+    if (FDT != V2E_DT_U8) bad = bad || ((float)v != x);
+    return v;
+}
+
+template <int NOISE>
+struct SpPx {   // one pixel after the frame loop
+    float nw[kSpNF], dl[NOISE == 1 ? kSpNF : 1];
+    float lp, base, base0, tm;
+    unsigned w0, w1, w2;   // the packed shot fields (call B of the pixel's noise block)
+    bool act, cand, bad, allcand;
+};
+
+// The frame loop of one pixel (v2e_model.py:321-322,332,350-404 up to the threshold test):
+// everything the frames present to the pixel whatever it does.
+template <int FDT, int R, int NOISE, bool CUTOFF>
+__device__ __forceinline__ void sp_stream_px(SpPx<NOISE>& o, const float (&x)[kSpNF], float x0,
+                                             float pos, float neg, float nra, float base_in,
+                                             float lp_in, float tm_in, bool small, unsigned p,
+                                             const CfgDev& cfg, const SeqDev& sq,
+                                             const float2* s_lut, const FrameSc* s_fr,
+                                             float kmax4) {
+    bool bad = false;
+    float base, lp, tm;
+    if (sq.first_pack) {
+        // _init (v2e_model.py:156-174,239-240)
+        base = s_lut[sp_index<FDT>(x0, bad)].x;
+        lp = base;
+        tm = fadd(0.f, -sq.Tr);
+    } else {
+        base = base_in;
+        lp = lp_in;
+        tm = tm_in;
+        // pack rollover (v2e_model.py:329-330)
+        if (tm > 0.f) tm = fsub(tm, sq.bins_m1);
+        if (tm < 0.f) tm = -sq.Tr;
+    }
+    o.base0 = base;
+    // crossing a threshold needs |diff| >= C + 1e-9 for the polarity's C (v2e_model.py:403-404):
+    // below the smaller of the two nothing can happen
+    const float dmin = fminf(fadd(pos, 1e-9f), fadd(neg, 1e-9f));
+    uint4 wa = make_uint4(0, 0, 0, 0), wb = make_uint4(0, 0, 0, 0);
+    float nlk = 0.f;
+    if (NOISE == 1) {
+        wa = noise_px<R>(sq.philox_ctr, p, 0u, 0);
+        wb = noise_px<R>(sq.philox_ctr, p, 0u, 1);
+        nlk = fmul(cfg.leak_rate, nra);
+    }
+    const float jit = cfg.leak_jitter;
+    bool act = false;
+    float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSpNF; ++k) {
+        const FrameSc& fs = s_fr[k + 1];
+        const float2 li = s_lut[sp_index<FDT>(x[k], bad)];
+        float nwk = li.x;
+        if (CUTOFF) {
+            lp = lowpass(lp, li.x, li.y, small ? fs.s_small : fs.s_large);
+            nwk = lp;
+        }
+        o.nw[k] = nwk;
+        float b = base;
+        if (NOISE == 1) {
+            if ((k & 1) == 0) box_muller16(k < 8 ? (&wa.x)[k >> 1] : wb.w, z0, z1);
+            const float dlk = leak_dec(nlk, jit, (k & 1) ? z1 : z0, fs.sdt, pos);
+            o.dl[k] = dlk;
+            b = fsub(base, dlk);
+        }
+        act = act || fabsf(fsub(nwk, b)) >= dmin;
+        base = b;
+    }
+    o.lp = lp;
+    o.base = base;
+    o.tm = tm;
+    o.act = act;
+    o.bad = bad;
+    o.cand = false;
+    o.allcand = false;
+    o.w0 = wb.x & 0x3fffffffu;
+    o.w1 = wb.y & 0x3fffffffu;
+    o.w2 = wb.z & 0x3fffffffu;
+    if (NOISE == 1) {
+        // A frame can hold a shot event only if its field is below 1024*bound (fx_shot_thr).
+        // While that is <= 1 for this pixel (any practical rate) the nine tests collapse into
+        // "does any 10-bit field equal zero", three instructions per word.
+        o.allcand = !(kmax4 * fmaxf(pos, neg) <= 1.0f);
+        const unsigned L = 0x00100401u, H = 0x20080200u;
+        const unsigned zf = (((o.w0 - L) & ~o.w0) | ((o.w1 - L) & ~o.w1) | ((o.w2 - L) & ~o.w2)) & H;
+        o.cand = zf != 0u || o.allcand;
+    }
+}
+
+struct SpAcc {   // per-lane accumulators of a resolve round
+    unsigned nnz, nev;
+    long long s1;
+    unsigned long long lo, hi;
+};
+
+template <int FDT, int R, int NOISE, bool CUTOFF>
+__global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_constant__ FxParams prm) {
+    constexpr bool LEAK = NOISE == 1, SHOT = NOISE == 1;
+    constexpr int T = kFxSpecT, nb = kFxSpecNb;
+    constexpr int cap = fx_spec_cap(LEAK);
+    constexpr int nw_off = FX_V0 + nb, dl_off = nw_off + kSpNF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const CfgDev& cfg = prm.cfg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seq = blockIdx.x / prm.tiles_per_seq;
+    const int tile = blockIdx.x - seq * prm.tiles_per_seq;
+    // this sequence's launch record -> shared memory
+    const FxSeqBlock* blk = prm.blocks ? prm.blocks + seq : &prm.one;
+    {
+        unsigned* d_sq = (unsigned*)(smem_raw + 3840);
+        const unsigned* s_sq = (const unsigned*)&blk->sq;
+        for (int i = tid; i < (int)(sizeof(SeqDev) / 4); i += kFxThreads) d_sq[i] = s_sq[i];
+        unsigned* d_fr = (unsigned*)(smem_raw + 2048);
+        const unsigned* s_fr0 = (const unsigned*)&blk->fr[0];
+        for (int i = tid; i < (int)(sizeof(FrameSc) * T / 4); i += kFxThreads) d_fr[i] = s_fr0[i];
+    }
+    __syncthreads();
+    const SeqDev& sq = *(const SeqDev*)(smem_raw + 3840);
+    FxWork& fx = prm.fx[seq];
+    const int P = cfg.P;
+    const bool normalise = cfg.output_mode == V2E_OUT_VOXEL;
+
+    // ---- shared memory carve-up (header layout of v2e_fixpoint.cu) --------------------------------
+    float2* s_lut = (float2*)smem_raw;                                   // 2048
+    FrameSc* s_fr = (FrameSc*)(smem_raw + 2048);                         // 10 * 32
+    SpFrameEv* s_ev = (SpFrameEv*)(smem_raw + 2368);                     // 10 * 32
+    FrameGlobals* s_g = (FrameGlobals*)(smem_raw + 3072);                // 32 * 12 = 384
+    unsigned* s_max = (unsigned*)(smem_raw + 3456);                      // 128: this tile, this round
+    unsigned* s_gmax = (unsigned*)(smem_raw + 3584);                     // 128: all tiles
+    unsigned long long* s_acc = (unsigned long long*)(smem_raw + 3712);  // 5 * 8: tile partials
+    unsigned long long* s_tot = (unsigned long long*)(smem_raw + 3752);  // 5 * 8: sequence totals
+    int* s_cnt = (int*)(smem_raw + 3792);   // [0] slot counter, [1] spilled, [2] error, [3] entries, [5] task counter
+    float* s_stat = (float*)(smem_raw + 3824);                           // mean, den, on, theta
+    unsigned short* s_perm = (unsigned short*)(smem_raw + kFxPermOff);
+    int* s_hist = (int*)(smem_raw + kFxPermOff + 2 * kFxPermMax);        // 2 x 64 ints
+    unsigned* s_ent = (unsigned*)(smem_raw + kFxHeader);
+    FxSmem sm;
+    sm.lut = s_lut; sm.fr = s_fr; sm.g = s_g; sm.max = s_max; sm.acc = s_acc; sm.perm = s_perm; sm.tl = nullptr;
+
+    const int tile_px0 = tile * prm.tile_px;
+    const int tile_n = max(0, min(prm.tile_px, P - tile_px0));   // even (P and tile_px are)
+    unsigned* spill_list = prm.spill_list + (size_t)seq * P + tile_px0;
+    float* spill_vox = prm.spill_vox + (size_t)seq * nb * P;
+    float* spill_state = prm.spill_state + (size_t)seq * 3 * P;
+
+    // development aid (V2E_TIMELINE=1): stamps are kept in shared memory and written out at the end
+    long long* tl_out = prm.timeline ? prm.timeline + (size_t)blockIdx.x * 32 : nullptr;
+    long long* tl = tl_out ? (long long*)(smem_raw + 2688) : nullptr;
+    if (tl && tid < 32) tl[tid] = 0;
+    __syncthreads();
+    FX_STAMP(0);
+    if (prm.timeline && blockIdx.x == 0 && tid == 0)
+        prm.timeline[160 * 32 + 2 * (fx.pad[0] & 127u)] = fx_now();
+    load_lut(s_lut, cfg.lut);
+    auto set_globals = [&](int n, int mx) {
+        const FrameGlobals g = frame_globals(mx, sq.duration, sq.Tr);
+        s_g[n] = g;
+        SpFrameEv e;
+        e.t0 = s_fr[n].t_bin_prev;
+        e.step = g.ts_step;
+        e.rstep = __fdividef(1.0f, g.ts_step);
+        e.mxf = (float)mx;
+        e.ts1 = fadd(e.t0, g.ts_step);   // iteration 0: step * 1 is exact (:419)
+        const float ti = floorf(e.ts1);
+        const float d = fsub(e.ts1, ti);
+        e.bbf = ti;
+        e.wl = fsub(1.0f, d);
+        e.wr = d;
+        s_ev[n] = e;
+    };
+    if (tid < V2E_MAX_FRAMES) {
+        // the guess: last pack's maxima (a hint kept in the workspace; any value is correct)
+        const unsigned h = fx.guess[tid];
+        if (tid < T) set_globals(tid, h ? (int)h - 1 : 8);
+        s_max[tid] = 0;
+        s_gmax[tid] = 0;
+    }
+    if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
+    if (tid < 8) s_cnt[tid] = 0;
+    if (tid < 128) s_hist[tid] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        int gmin = 0x7fffffff;
+        float kmax = 0.f;
+        for (int n = 1; n < T; ++n) {
+            gmin = min(gmin, s_g[n].mx);
+            kmax = fmaxf(kmax, fmaxf(s_fr[n].kp, s_fr[n].kn));
+        }
+        s_stat[3] = (float)max(2, gmin / 2);   // theta of the "hot" test
+        // 1024 * bound <= kmax4 * C: fx_shot_thr with its intensity factor (<= 1) dropped
+        s_stat[2] = kmax * 4.0f;
+    }
+    __syncthreads();
+    const float theta = s_stat[3];
+    const float kmax4 = s_stat[2];
+
+    FX_STAMP(1);
+    // ================================ pass 1: stream ===============================================
+    for (int c0 = warp * 64; c0 < tile_n; c0 += kFxThreads * 2) {
+        const bool valid = c0 + 2 * lane < tile_n;
+        const int l = min(c0 + 2 * lane, tile_n - 2);   // lanes past the end shadow the last pair
+        const int p = tile_px0 + l;
+        const float2 pos2 = __ldg((const float2*)(sq.pos + p));
+        const float2 neg2 = __ldg((const float2*)(sq.neg + p));
+        float2 nra2 = make_float2(0.f, 0.f), base2 = nra2, lp2 = nra2, tm2 = nra2, x02 = nra2;
+        if (LEAK) nra2 = __ldg((const float2*)(sq.nra + p));
+        if (sq.first_pack) {
+            x02 = sp_load_frame2<FDT>(sq.frames, p);
+        } else {
+            base2 = *(const float2*)(sq.base + p);
+            if (CUTOFF) lp2 = *(const float2*)(sq.lp + p);
+            tm2 = *(const float2*)(sq.tmem + p);
+        }
+        float2 x2[kSpNF];
+#pragma unroll
+        for (int k = 0; k < kSpNF; ++k) x2[k] = sp_load_frame2<FDT>(sq.frames, (long long)(k + 1) * P + p);
+        // sensing-diversity pattern: even row AND even column (v2e_model.py:194,211); W is even,
+        // so only the pair's first pixel can sit on an even column
+        const int yrow = p / cfg.W;
+        const bool small0 = ((yrow | (p - yrow * cfg.W)) & 1) == 0;
+
+        float lp_out[2], base_out[2], tm_out[2];
+        bool quiet[2], spilled[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float x[kSpNF];
+#pragma unroll
+            for (int k = 0; k < kSpNF; ++k) x[k] = j ? x2[k].y : x2[k].x;
+            SpPx<NOISE> o;
+            sp_stream_px<FDT, R, NOISE, CUTOFF>(o, x, j ? x02.y : x02.x, j ? pos2.y : pos2.x,
+                                                j ? neg2.y : neg2.x, j ? nra2.y : nra2.x,
+                                                j ? base2.y : base2.x, j ? lp2.y : lp2.x,
+                                                j ? tm2.y : tm2.x, j ? false : small0,
+                                                (unsigned)(p + j), cfg, sq, s_lut, s_fr, kmax4);
+            // ---- quiet -> finished; maybe active -> table entry (or spill when the table is full)
+            const bool want = valid && (o.act || o.cand) && !o.bad;
+            const unsigned am = __ballot_sync(0xffffffffu, want);
+            int slot = -1;
+            if (am) {
+                int s0 = 0;
+                if (lane == 0) {
+                    s0 = atomicAdd(&s_cnt[0], __popc(am));
+                    if (s0 + __popc(am) <= cap) atomicMax(&s_cnt[3], s0 + __popc(am));
+                }
+                s0 = __shfl_sync(0xffffffffu, s0, 0);
+                if (want && s0 + __popc(am) <= cap) slot = s0 + __popc(am & ((1u << lane) - 1u));
+            }
+            const bool spill = valid && (o.bad || (want && slot < 0));
+            const unsigned spm = __ballot_sync(0xffffffffu, spill);
+            if (spm) {
+                int s0 = 0;
+                if (lane == 0) s0 = atomicAdd(&s_cnt[1], __popc(spm));
+                s0 = __shfl_sync(0xffffffffu, s0, 0);
+                if (spill) spill_list[s0 + __popc(spm & ((1u << lane) - 1u))] = (unsigned)(l + j);
+            }
+            if (slot >= 0) {
+                unsigned cm = 0;
+                if (SHOT && o.cand) {
+                    if (o.allcand) {
+                        cm = 0x1ffu;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kSpNF; ++k) {
+                            const unsigned w = k < 3 ? o.w0 : (k < 6 ? o.w1 : o.w2);
+                            if (((w >> (10 * (k % 3))) & 1023u) == 0u) cm |= 1u << k;
+                        }
+                    }
+                }
+                unsigned* e = s_ent + slot;
+                // first active frame 0: found by the post pass
+                e[FX_META * cap] = (o.tm == 0.f ? 32u : 0u) | (cm << 6);
+                e[FX_IDX * cap] = (unsigned)(l + j);
+                e[FX_BASE * cap] = __float_as_uint(o.base0);
+                e[FX_POS * cap] = __float_as_uint(j ? pos2.y : pos2.x);
+                e[FX_NEG * cap] = __float_as_uint(j ? neg2.y : neg2.x);
+#pragma unroll
+                for (int k = 0; k < kSpNF; ++k) {
+                    e[(nw_off + k) * cap] = __float_as_uint(o.nw[k]);
+                    if (LEAK) e[(dl_off + k) * cap] = __float_as_uint(o.dl[k]);
+                }
+            }
+            lp_out[j] = o.lp;
+            base_out[j] = o.base;
+            tm_out[j] = o.tm;
+            spilled[j] = spill;
+            quiet[j] = valid && !spill && slot < 0;
+        }
+#ifdef SP_EXP_NOSTORE
+        if (valid && prm.timeline == (long long*)1) {
+#else
+        if (valid) {
+#endif
+            // no event ever touches the low-pass state: final for every pixel that is not spilled
+            // (the spill path recomputes a pixel from its stored state)
+            if (CUTOFF) {
+                if (!spilled[0] && !spilled[1]) {
+                    *(float2*)(sq.lp + p) = make_float2(lp_out[0], lp_out[1]);
+                } else {
+                    if (!spilled[0]) sq.lp[p] = lp_out[0];
+                    if (!spilled[1]) sq.lp[p + 1] = lp_out[1];
+                }
+            }
+            if (quiet[0] && quiet[1]) {
+                *(float2*)(sq.base + p) = make_float2(base_out[0], base_out[1]);
+                *(float2*)(sq.tmem + p) = make_float2(tm_out[0], tm_out[1]);
+            } else {
+                if (quiet[0]) { sq.base[p] = base_out[0]; sq.tmem[p] = tm_out[0]; }
+                if (quiet[1]) { sq.base[p + 1] = base_out[1]; sq.tmem[p + 1] = tm_out[1]; }
+            }
+            // zero voxel columns; the commit overwrites those of the active pixels
+#ifdef SP_EXP_NOVOX
+            if (prm.timeline == (long long*)1)
+#endif
+#pragma unroll
+            for (int b = 0; b < nb; ++b) {
+                if (cfg.voxel_bf16) *(unsigned*)((__nv_bfloat16*)sq.voxel + (size_t)b * P + p) = 0u;
+                else *(float2*)((float*)sq.voxel + (size_t)b * P + p) = make_float2(0.f, 0.f);
+            }
+        }
+    }
+    __syncthreads();
+    const int n_ent = s_cnt[3];
+    const int n_spill = s_cnt[1];
+    // ================================ post pass over the table =====================================
+    // first active frame f (exact test, v2e_model.py:394-404), brightness before it, "hot" flag:
+    // some frame is theta thresholds away from the brightness the entry starts with - a bound no
+    // event count of the pixel exceeds by much.  Scheduling hint only: the hot entries alone
+    // usually decide the per-frame maxima (pre-pass below).
+    for (int i = tid; i < n_ent; i += kFxThreads) {
+        unsigned* ep = s_ent + i;
+        const unsigned meta = ep[FX_META * cap];
+        const unsigned cm = (meta >> 6) & 0x3ffu;
+        const float pos = __uint_as_float(ep[FX_POS * cap]), neg = __uint_as_float(ep[FX_NEG * cap]);
+        float base = __uint_as_float(ep[FX_BASE * cap]);
+        const float base0 = base;
+        int f = 0;
+        float sb = 0.f;
+        bool hot = false;
+#pragma unroll
+        for (int k = 0; k < kSpNF; ++k) {
+            const float nw = __uint_as_float(ep[(nw_off + k) * cap]);
+            const float b = LEAK ? fsub(base, __uint_as_float(ep[(dl_off + k) * cap])) : base;
+            const float diff = fsub(nw, b);
+            const float ad = fabsf(diff);
+            const bool up = diff > 0.f;
+            const float den = fadd(up ? pos : neg, 1e-9f);
+            const bool hit = !f && ad > 1e-6f && (ad >= den || ((cm >> k) & 1u));
+            if (hit) { f = k + 1; sb = base; }
+            const float d0 = fsub(nw, base0);
+            hot = hot || fabsf(d0) >= theta * (d0 > 0.f ? pos : neg);
+            if (!f) base = b;
+        }
+        if (!f) { f = 31; sb = base; }   // nothing happens after all: the entry only carries its state
+        ep[FX_META * cap] = meta | (unsigned)f | (hot ? 0x10000u : 0u);
+        ep[FX_BASE * cap] = __float_as_uint(sb);
+        atomicAdd(&s_hist[(hot ? 32 : 0) + f], 1);
+    }
+    __syncthreads();
+    // ---- order the entries by first active frame (counting sort; order within a frame is free) ---
+    if (tid == 0) {
+        int o = 0;
+        for (int i = 0; i < 64; ++i) {   // cold frames 0..31, then hot frames 0..31
+            const int c = s_hist[i];
+            s_hist[64 + i] = o;
+            o += c;
+            if (i == 31) s_cnt[4] = o;   // cold entries
+        }
+    }
+    __syncthreads();
+    const int n_cold = s_cnt[4], n_hot = n_ent - n_cold;
+    for (int i = tid; i < n_ent; i += kFxThreads) {
+        const unsigned meta = s_ent[FX_META * cap + i];
+        s_perm[atomicAdd(&s_hist[64 + ((meta & 0x10000u) ? 32 : 0) + (int)(meta & 31u)], 1)] = (unsigned short)i;
+    }
+    __syncthreads();
+    FX_STAMP(2);
+    if (tl && tid == 0) { tl[28] = n_ent; tl[29] = n_spill; tl[26] = n_hot; }
+
+    // ================================ resolve rounds ================================================
+    // round 0 is a pre-pass over the hot entries only: under last pack's guess it yields the
+    // maxima those entries reach, which are nearly always the image-wide ones - the guess of the
+    // first full round.  Rounds >= 1 resolve every entry and test the guess they ran under.
+    const float Tr = sq.Tr;
+    int pass = 0;
+    bool converged = false;
+    for (; pass < T + 3; ++pass) {
+        const bool pre = pass == 0;
+        SpAcc acc;
+        acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
+        if (pre) {
+            // The pre-pass only has to produce a good guess, and every warp of the grid waits for
+            // its dependent chain of frames: one hot entry per lane, straight-line code, no voxel
+            // accumulation, shot candidates ignored, every event frame taken as the usual single
+            // event (gate on) or the plain count (gate off).
+            for (int i0 = warp * 32; i0 < n_hot; i0 += kFxThreads) {
+                const int i = i0 + lane;
+                const bool on = i < n_hot;
+                const unsigned* ep = s_ent + s_perm[n_cold + (on ? i : 0)];
+                const unsigned meta = ep[FX_META * cap];
+                float base = __uint_as_float(ep[FX_BASE * cap]);
+                float tm = (meta & 32u) ? 0.f : -Tr;
+                const float pos = __uint_as_float(ep[FX_POS * cap]);
+                const float neg = __uint_as_float(ep[FX_NEG * cap]);
+                const float denp = fadd(pos, 1e-9f), denn = fadd(neg, 1e-9f);
+                const int f = on ? (int)(meta & 31u) : V2E_MAX_FRAMES;
+                const int n_first = __reduce_min_sync(0xffffffffu, f);
+                const unsigned* nwp = ep + (nw_off + n_first - 1) * cap;
+#pragma unroll 1
+                for (int n = n_first; n < T; ++n, nwp += cap) {
+                    const bool act = n >= f;
+                    const SpFrameEv ev = s_ev[n];
+                    const bool gate = s_g[n].gate != 0;
+                    const float b = LEAK ? fsub(base, __uint_as_float(nwp[kSpNF * cap])) : base;
+                    const float diff = fsub(__uint_as_float(nwp[0]), b);
+                    const float ad = fabsf(diff);
+                    const bool up = diff > 0.f;
+                    const float den = up ? denp : denn;
+                    const bool cross = act && ad >= den;
+                    if (act) base = b;
+                    const float cntf = cross ? floorf(fdiv(ad, den)) : 0.f;   // event_counts (:404)
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)(int)cntf);
+                    if (wmax > s_max[n] && lane == 0) atomicMax(&s_max[n], wmax);
+                    const float cf = fminf(cntf, ev.mxf);
+                    const float tc = fadd(ev.t0, fmul(ev.step, cf));
+                    const bool first = fsub(ev.ts1, tm) > Tr;
+                    float jl = floorf((Tr + tm - ev.t0) * ev.rstep - 0.5f);
+                    jl = fmaxf(fminf(jl, cf - 1.f), 1.f);
+                    const float tsb = fadd(ev.t0, fmul(ev.step, jl + 1.f));
+                    const float tsc = fadd(ev.t0, fmul(ev.step, jl + 2.f));
+                    const float ts = first ? ev.ts1 : (fsub(tsb, tm) > Tr ? tsb : tsc);
+                    const float C = up ? pos : neg;
+                    if (gate) {
+                        if (cf >= 1.f && fsub(tc, tm) > Tr) {
+                            tm = ts;
+                            base = fadd(base, up ? C : -C);
+                        }
+                    } else if (cf >= 1.f) {
+                        base = fadd(base, fmul(fmul(up ? 1.f : -1.f, cf), C));
+                    }
+                }
+            }
+        } else {
+            // tasks drawn from a queue: the hot list first (short tasks of kSpHotLanes entries:
+            // a hot entry has events in most frames and a warp walks the union of its lanes'
+            // paths, so fewer lanes per warp shorten the chain every round waits for), then the
+            // cold list in tasks of 32; each list in the order of the first active frame, so that
+            // a task only walks the frames its entries need
+            const int th = (n_hot + kSpHotLanes - 1) / kSpHotLanes, tc = (n_cold + 31) >> 5;
+            while (true) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(&s_cnt[5], 1);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= th + tc) break;
+                int e;
+                bool on;
+                if (t < th) {
+                    const int i = t * kSpHotLanes + lane;
+                    on = lane < kSpHotLanes && i < n_hot;
+                    e = s_perm[n_cold + (on ? i : 0)];
+                } else {
+                    const int i = (t - th) * 32 + lane;
+                    on = i < n_cold;
+                    e = s_perm[on ? i : 0];
+                }
+                unsigned* ep = s_ent + e;
+                const unsigned meta = ep[FX_META * cap];
+                const int p = tile_px0 + (int)ep[FX_IDX * cap];
+                const unsigned cm = SHOT ? (meta >> 6) & 0x1ffu : 0u;
+                float base = __uint_as_float(ep[FX_BASE * cap]);
+                float tm = (meta & 32u) ? 0.f : -Tr;
+                const float pos = __uint_as_float(ep[FX_POS * cap]);
+                const float neg = __uint_as_float(ep[FX_NEG * cap]);
+                const float denp = fadd(pos, 1e-9f), denn = fadd(neg, 1e-9f);
+                const int f = on ? (int)(meta & 31u) : V2E_MAX_FRAMES;
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f;
+                unsigned nev = 0;
+                const int n_first = __reduce_min_sync(0xffffffffu, f);
+                const unsigned* nwp = ep + (nw_off + n_first - 1) * cap;
+#pragma unroll 1
+                for (int n = n_first; n < T; ++n, nwp += cap) {
+#ifdef SP_EXP_STAMPS
+                    if (tl && pass == 0 && t == 0 && lane == 0) tl[13 + n] = fx_now();
+#endif
+                    const bool act = n >= f;
+                    const float b = LEAK ? fsub(base, __uint_as_float(nwp[kSpNF * cap])) : base;
+                    const float diff = fsub(__uint_as_float(nwp[0]), b);
+                    const float ad = fabsf(diff);
+                    const bool up = diff > 0.f;
+                    const float den = up ? denp : denn;
+                    const bool cross = act && ad >= den;   // den > 1e-6: the tolerance mask (:394) holds
+                    const bool bit = SHOT && act && ((cm >> (n - 1)) & 1u) && ad > 1e-6f;
+                    if (act) base = b;
+                    if (!__any_sync(0xffffffffu, cross || bit)) continue;   // a quiet frame for the whole task
+                    // event_counts (:404): 1 below twice the denominator (exact), else the quotient
+                    // (warp-uniform branch: cold tasks hardly ever divide)
+                    const bool big = cross && !(ad < fadd(den, den));
+                    float cntf = cross ? 1.f : 0.f;
+                    if (__any_sync(0xffffffffu, big)) {
+                        if (big) cntf = floorf(fdiv(ad, den));
+                    }
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)(int)cntf);
+                    if (wmax > s_max[n] && lane == 0) atomicMax(&s_max[n], wmax);
+                    if (cross || bit) {
+                        const SpFrameEv ev = s_ev[n];
+                        const bool gate = s_g[n].gate != 0;
+                        const float C = up ? pos : neg;
+                        // What the iteration loop (v2e_model.py:449-475) does to this pixel, for the
+                        // usual outcomes - no event or exactly one - without walking it.  Iteration
+                        // j of [0,c) carries an event; with the gate on (:469) it is accepted iff
+                        // ts_j - timestamp_mem > Tr (:419,:470), monotone in j.
+                        const float cf = fminf(cntf, ev.mxf);
+                        const float tc = fadd(ev.t0, fmul(ev.step, cf));        // stamp of iteration c-1
+                        const bool first = !gate || fsub(ev.ts1, tm) > Tr;      // iteration 0 passes
+                        // else the first iteration that can pass, from an estimate: iteration j
+                        // passes iff step * (j + 1) > Tr + timestamp_mem - t0 =: X, so the first
+                        // one is floor(X / step).  X / step sits next to an integer whenever the
+                        // maxima of consecutive frames are commensurable (the usual case), so two
+                        // neighbours are tried, each with the exact predicate.
+                        float jl = floorf((Tr + tm - ev.t0) * ev.rstep - 0.5f);
+                        jl = fmaxf(fminf(jl, cf - 1.f), 1.f);
+                        const float tsa = fadd(ev.t0, fmul(ev.step, jl));         // iteration jl-1
+                        const float tsb = fadd(ev.t0, fmul(ev.step, jl + 1.f));   // iteration jl
+                        const float tsc = fadd(ev.t0, fmul(ev.step, jl + 2.f));   // iteration jl+1
+                        const bool pb = fsub(tsb, tm) > Tr;
+                        const bool any = cf >= 1.f && (!gate || fsub(tc, tm) > Tr);
+                        const bool est = cf >= 2.f && !(fsub(tsa, tm) > Tr) &&
+                                         (pb || (jl + 2.f <= cf && fsub(tsc, tm) > Tr));
+                        const float ts = first ? ev.ts1 : (pb ? tsb : tsc);
+                        const float nxt = first ? 1.f : (pb ? jl + 1.f : jl + 2.f);   // iterations consumed
+                        // one more after it?  (gate off: every iteration is an event)
+                        const bool more = nxt < cf && (!gate || fsub(tc, ts) > Tr);
+                        int fin = 0;
+                        if (bit || (any && ((!first && !est) || more))) {
+                            // shot candidates, several events in the frame, estimate off: the
+                            // generic code, accumulators via the entry's voxel words
+#ifdef SP_EXP_STAMPS
+                            if (tl && pass == 0)
+                                atomicAdd((unsigned long long*)&tl[24], bit ? 1ull : more ? (1ull << 16) : (1ull << 32));
+#endif
+                            float* vp = (float*)(ep + FX_V0 * cap);
+                            vp[0] = v0; vp[cap] = v1; vp[2 * cap] = v2; vp[3 * cap] = v3; vp[4 * cap] = v4;
+                            const unsigned long long r = fx_event_frame<FDT, R, false>(
+                                prm, sq, sm, n, p, (int)cntf, up ? 1.f : -1.f, C, bit, SHOT, NOISE == 1, tm,
+                                vp, cap);
+                            fin = (int)(r >> 32);
+                            tm = __uint_as_float((unsigned)r);
+                            v0 = vp[0]; v1 = vp[cap]; v2 = vp[2 * cap]; v3 = vp[3 * cap]; v4 = vp[4 * cap];
+                            if (fin) base = fadd(base, fmul(fmul(up ? 1.f : -1.f, (float)fin), C));   // :522
+                        } else if (any) {
+                            // exactly one event, at ts (:478-502); pol * w is w or -w
+                            fin = 1;
+                            if (gate) tm = ts;
+                            float bbf = ev.bbf, wl = ev.wl, wr = ev.wr;
+                            if (!first) {
+                                bbf = floorf(ts);
+                                wr = fsub(ts, bbf);
+                                wl = fsub(1.0f, wr);
+                            }
+                            if (!up) { wl = -wl; wr = -wr; }
+                            if (bbf == 0.f) { v0 = fadd(v0, wl); v1 = fadd(v1, wr); }
+                            else if (bbf == 1.f) { v1 = fadd(v1, wl); v2 = fadd(v2, wr); }
+                            else if (bbf == 2.f) { v2 = fadd(v2, wl); v3 = fadd(v3, wr); }
+                            else if (bbf == 3.f) { v3 = fadd(v3, wl); v4 = fadd(v4, wr); }
+                            else if (bbf == 4.f) { v4 = fadd(v4, wl); }
+                            base = fadd(base, up ? C : -C);   // :522: (pol * 1) * C
+                        }
+                        nev += (unsigned)fin;
+                    }
+                }
+#ifdef SP_EXP_STAMPS
+                if (tl && pass == 0 && t == 0 && lane == 0) tl[23] = fx_now();
+#endif
+                if (on) {
+                    ep[FX_OB * cap] = __float_as_uint(base);
+                    ep[FX_OT * cap] = __float_as_uint(tm);
+                    ep[(FX_V0 + 0) * cap] = __float_as_uint(v0);
+                    ep[(FX_V0 + 1) * cap] = __float_as_uint(v1);
+                    ep[(FX_V0 + 2) * cap] = __float_as_uint(v2);
+                    ep[(FX_V0 + 3) * cap] = __float_as_uint(v3);
+                    ep[(FX_V0 + 4) * cap] = __float_as_uint(v4);
+                    acc.nev += nev;
+                    fx_stat(v0, acc.nnz, acc.s1, acc.lo, acc.hi);
+                    fx_stat(v1, acc.nnz, acc.s1, acc.lo, acc.hi);
+                    fx_stat(v2, acc.nnz, acc.s1, acc.lo, acc.hi);
+                    fx_stat(v3, acc.nnz, acc.s1, acc.lo, acc.hi);
+                    fx_stat(v4, acc.nnz, acc.s1, acc.lo, acc.hi);
+                }
+            }
+            FxAcc a;
+            a.nnz = acc.nnz; a.nev = acc.nev; a.s1 = acc.s1; a.lo = acc.lo; a.hi = acc.hi;
+            fx_flush(a, s_acc);
+        }
+        if (n_spill && !pre)
+            fx_resolve_spill<FDT, R, false, true>(prm, sq, sm, spill_list, n_spill, tile_px0, spill_vox,
+                                                  spill_state, LEAK, SHOT, NOISE == 1, CUTOFF);
+        __syncthreads();
+        if (pass < 4) FX_STAMP(3 + 3 * pass);
+        // ---- grid barrier of this sequence: accumulate (maxima, partials), arrive, wait, read ------
+        {
+            unsigned* gm = fx.gmax[pass];
+            unsigned long long* gs = fx.stat[pass];
+#ifdef SP_EXP_NOATOM
+            if (prm.timeline != (long long*)1) {
+            } else
+#endif
+            if (tid >= 1 && tid < T) {
+                if (s_max[tid]) atomicMax(gm + tid, s_max[tid]);
+            } else if (tid >= 32 && tid < 38) {
+                // nnz, sum, the 128-bit sum of squares as three 40-bit limbs, events
+                const unsigned long long lo = s_acc[2], hi = s_acc[3];
+                const int k = tid - 32;
+                const unsigned long long v =
+                    k == 0 ? s_acc[0] : k == 1 ? s_acc[1] : k == 2 ? (lo & 0xffffffffffull)
+                    : k == 3 ? ((lo >> 40) | ((hi & 0xffffull) << 24)) : k == 4 ? (hi >> 16) : s_acc[4];
+                if (v) atomicAdd(gs + k, v);
+            }
+            __syncthreads();
+            if (tid == 0) {
+#ifdef SP_EXP_RELAXED
+                atomicAdd(&fx.arrive, 1u);
+#else
+                fx_red_release_add(&fx.arrive, 1u);
+#endif
+                if (tl && pass < 3) tl[5 + 3 * pass] = fx_now();
+                const unsigned target = (unsigned)prm.tiles_per_seq * ((unsigned)pass + 1u);
+                int spins = 0;
+                while (fx_ld_acquire(&fx.arrive) < target)
+                    if (++spins > kFxSpin) { s_cnt[2] = 1; break; }
+            }
+            __syncthreads();
+            if (tid >= 1 && tid < T) {
+                s_gmax[tid] = fx_ld_relaxed(gm + tid);
+            } else if (tid == 32) {
+                unsigned long long q[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) q[k] = fx_ld_relaxed64(gs + k);
+                const unsigned long long lo = q[2] + (q[3] << 40);
+                s_tot[0] = q[0];
+                s_tot[1] = q[1];
+                s_tot[2] = lo;
+                s_tot[3] = (q[3] >> 24) + (q[4] << 16) + (lo < q[2] ? 1ull : 0ull);
+                s_tot[4] = q[5];
+            }
+        }
+        __syncthreads();
+        if (pass < 4) FX_STAMP(4 + 3 * pass);
+        // ---- m == g ? ------------------------------------------------------------------------------
+        const int changed = __syncthreads_or(tid >= 1 && tid < T && (int)s_gmax[tid] != s_g[tid].mx);
+        if (!pre && (!changed || s_cnt[2])) { converged = !changed; break; }
+        if (tid >= 1 && tid < T) {
+            // after the pre-pass a frame no hot entry fired in keeps last pack's guess
+            const int mx = (pre && s_gmax[tid] == 0) ? s_g[tid].mx : (int)s_gmax[tid];
+            set_globals(tid, mx);
+        }
+        if (tid < V2E_MAX_FRAMES) { s_max[tid] = 0; s_gmax[tid] = 0; }
+        if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
+        if (tid == 0) s_cnt[5] = 0;
+        __syncthreads();
+    }
+
+    FX_STAMP(27);
+    if (tl && tid == 0) tl[30] = pass + 1;   // rounds run, pre-pass included
+    // ================================ commit =========================================================
+    if (tid == 0) {
+        float mean = 0.f, den = 1.f, on = 0.f;
+        const double c = (double)s_tot[0];
+        if (c > 0. && normalise) {
+            // utils/event_process.py:166-175
+            const double a = (double)(long long)s_tot[1] * (1.0 / 2147483648.0);
+            const double b = ((double)s_tot[3] * 18446744073709551616.0 + (double)s_tot[2]) *
+                             (1.0 / 2147483648.0) * (1.0 / 2147483648.0);
+            mean = fdiv((float)a, (float)c);
+            den = fadd(sqrtf(fsub(fdiv((float)b, (float)c), fmul(mean, mean))), 1e-8f);
+            on = 1.f;
+        }
+        s_stat[0] = mean; s_stat[1] = den; s_stat[2] = on;
+        if (tile == 0) {
+            *sq.num_events = s_tot[4];
+            if (sq.status && (!converged || s_cnt[2])) *sq.status = V2E_STATUS_NOT_CONVERGED;
+        }
+    }
+    if (tile == 0 && tid >= 1 && tid < V2E_MAX_FRAMES) {
+        if (tid < T) {
+            if (sq.max_iters) sq.max_iters[tid] = (int)s_gmax[tid];
+            fx.guess[tid] = s_gmax[tid] + 1u;
+        } else {
+            fx.guess[tid] = 0u;
+        }
+    }
+    __syncthreads();
+    {
+        const float mean = s_stat[0], den = s_stat[1];
+        const bool norm = s_stat[2] != 0.f;
+        for (int i = tid; i < n_ent; i += kFxThreads) {
+            const unsigned* ep = s_ent + i;
+            const int p = tile_px0 + (int)ep[FX_IDX * cap];
+            sq.base[p] = __uint_as_float(ep[FX_OB * cap]);
+            sq.tmem[p] = __uint_as_float(ep[FX_OT * cap]);
+#pragma unroll
+            for (int b = 0; b < nb; ++b) {
+                float v = __uint_as_float(ep[(FX_V0 + b) * cap]);
+                if (v != 0.f || !norm) {
+                    if (norm) v = fdiv(fsub(v, mean), den);   // nz * (v - mean) / (std + 1e-8)
+                    fx_store_vox(cfg, sq.voxel, (size_t)b * P + p, v);
+                }
+            }
+        }
+        for (int e = tid; e < n_spill; e += kFxThreads) {
+            const int p = tile_px0 + (int)spill_list[e];
+            sq.base[p] = spill_state[p];
+            if (CUTOFF) sq.lp[p] = spill_state[(size_t)P + p];
+            sq.tmem[p] = spill_state[(size_t)2 * P + p];
+            for (int b = 0; b < nb; ++b) {
+                float v = spill_vox[(size_t)b * P + p];
+                if (norm) v = fdiv(fmul(v != 0.f ? 1.f : 0.f, fsub(v, mean)), den);
+                fx_store_vox(cfg, sq.voxel, (size_t)b * P + p, v);
+            }
+        }
+    }
+    FX_STAMP(31);
+    if (tl) {
+        __syncthreads();
+        if (tid < 32) tl_out[tid] = tl[tid];
+    }
+    // ---- leave the barrier words zeroed: the last CTA of the sequence to get here cleans up ----------
+    if (tid == 0) {
+        __threadfence();
+        s_cnt[0] = atomicAdd(&fx.exit_count, 1u) == (unsigned)prm.tiles_per_seq - 1u;
+    }
+    __syncthreads();
+    if (s_cnt[0]) {
+        const int used = min(pass + 1, kFxMaxRounds);
+        for (int i = tid; i < used * V2E_MAX_FRAMES; i += kFxThreads) (&fx.gmax[0][0])[i] = 0u;
+        for (int i = tid; i < used * 8; i += kFxThreads) (&fx.stat[0][0])[i] = 0ull;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            fx.exit_count = 0;
+            fx.arrive = 0;
+            if (prm.timeline && seq == 0) {
+                prm.timeline[160 * 32 + 2 * (fx.pad[0] & 127u) + 1] = fx_now();
+                fx.pad[0] += 1;
+            }
+        }
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+template <int FDT, int R, int NOISE, bool CUTOFF>
+static int launch_spec_v(const FxParams& prm, int grid, size_t smem, int optin, cudaStream_t st) {
+    static bool attr_set = false;  // one process drives one device (multi-GPU)
+    auto kern = k_fixpoint_spec<FDT, R, NOISE, CUTOFF>;
+    int rc = V2E_OK;
+    if (!attr_set) {
+        rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        if (rc != V2E_OK) return rc;
+        attr_set = true;
+    }
+    void* args[] = {(void*)&prm};
+    rc = cuda_ok(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(kFxThreads),
+                                             args, smem, st));
+    count_launch();
+    return rc;
+}
+
+template <int FDT>
+static int launch_spec_t(const FxParams& prm, int noise, bool cutoff, int rounds, int grid,
+                         size_t smem, int optin, cudaStream_t st) {
+#ifdef V2E_FX_DEV   // development builds: one Philox depth only (fewer instantiations to compile)
+#define SP_BY_ROUNDS(C) launch_spec_v<FDT, 10, 1, C>(prm, grid, smem, optin, st)
+#else
+#define SP_BY_ROUNDS(C)                                                           \
+    (rounds == 7 ? launch_spec_v<FDT, 7, 1, C>(prm, grid, smem, optin, st)        \
+                 : launch_spec_v<FDT, 10, 1, C>(prm, grid, smem, optin, st))
+#endif
+    (void)rounds;
+    if (noise == 0)
+        return cutoff ? launch_spec_v<FDT, 10, 0, true>(prm, grid, smem, optin, st)
+                      : launch_spec_v<FDT, 10, 0, false>(prm, grid, smem, optin, st);
+    return cutoff ? SP_BY_ROUNDS(true) : SP_BY_ROUNDS(false);
+#undef SP_BY_ROUNDS
+}
+
+int launch_fixpoint_spec(const FxParams& prm, int frame_dtype, int noise, bool cutoff, int rounds,
+                         int grid, size_t smem, int optin, cudaStream_t st) {
+    switch (frame_dtype) {
+#ifndef V2E_FX_DEV
+        case V2E_DT_U8: return launch_spec_t<V2E_DT_U8>(prm, noise, cutoff, rounds, grid, smem, optin, st);
+        case V2E_DT_BF16: return launch_spec_t<V2E_DT_BF16>(prm, noise, cutoff, rounds, grid, smem, optin, st);
+#else
+        case V2E_DT_U8: case V2E_DT_BF16: return V2E_ERR_UNSUPPORTED;
+#endif
+        default: return launch_spec_t<V2E_DT_F32>(prm, noise, cutoff, rounds, grid, smem, optin, st);
+    }
+}
+
+}  // namespace v2e
