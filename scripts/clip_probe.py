@@ -43,9 +43,14 @@ for rep in range(4):
     del out
 if os.environ.get("V2E_TIMELINE"):
     ws = em._workspace
-    n = 160 * 32 * 8 + 2048
+    n = 160 * 32 * 8 + 2048 + 1024
     tl = ws[ws.numel() - n:].view(torch.int64).cpu().numpy()
-    hist = tl[160 * 32:].reshape(128, 2)
+    hist = tl[160 * 32:160 * 32 + 256].reshape(128, 2)
+    rounds = tl[160 * 32 + 256:160 * 32 + 384]
+    dur_all = (hist[:, 1] - hist[:, 0]) / 1e3
+    for r in sorted(set(rounds[hist[:, 0] > 0].tolist())):
+        m = (hist[:, 0] > 0) & (rounds == r)
+        print(f"launches with {r} rounds (pre-pass included): {int(m.sum()):3d} of {int((hist[:,0]>0).sum())}, kernel mean {dur_all[m].mean():.1f} us")
     h = hist[hist[:, 0] > 0]
     h = h[np.argsort(h[:, 0])][-40:]
     dur = (h[:, 1] - h[:, 0]) / 1e3

@@ -17,7 +17,7 @@ for k, fr, tfr in gc.video(1, 5, T, H, W):
     em(fr.cuda(), tfr)
     torch.cuda.synchronize()
     ws = em._workspace
-    tl = ws[ws.numel() - (160 * 32 * 8 + 2048):].view(torch.int64).cpu().numpy()[:160 * 32].reshape(160, 32)
+    tl = ws[ws.numel() - (160 * 32 * 8 + 2048 + 1024):].view(torch.int64).cpu().numpy()[:160 * 32].reshape(160, 32)
     tl = tl[tl[:, 0] > 0]
     t0 = tl[:, 0].min()
     npass = int(tl[0, 30])
@@ -31,11 +31,15 @@ for k, fr, tfr in gc.video(1, 5, T, H, W):
         rows += [(f"resolve{ps} done", 3 + 3 * ps)] + ([(f"arrived{ps}", 5 + 3 * ps)] if ps < 3 else []) + [(f"barrier{ps} done", 4 + 3 * ps)]
     rows += [("loop exit", 27), ("commit done", 31)]
     if os.environ.get("V2E_STAMPS"):
-        fr = tl[:, 14:24].astype(np.float64)
-        ok = (fr > 0).all(axis=1)
+        fr = tl[:, 1:10].astype(np.float64)
+        end = tl[:, 19].astype(np.float64)
+        ok = (fr > 0).all(axis=1) & (end > 0)
         if ok.any():
-            d = np.diff(fr[ok], axis=1) / 1e3
-            print("   pre-pass task 0, per frame (us): " + " ".join(f"{x:.2f}" for x in d.mean(axis=0)) + f"   | slow-path calls/tile in the pre-pass: shot {(tl[:,24] & 0xffff).mean():.1f} more {((tl[:,24] >> 16) & 0xffff).mean():.1f} est {(tl[:,24] >> 32).mean():.1f}")
+            d = np.diff(np.concatenate([fr[ok], end[ok, None]], axis=1), axis=1) / 1e3
+            print("   round 1, first cold task, per frame (us): " + " ".join(f"{x:.2f}" for x in d.mean(axis=0)) +
+                  f"   | non-simple event lanes/tile: general {(tl[:,24] & 0xffffffff).mean():.1f} slow {(tl[:,24] >> 32).mean():.1f}")
+        rows = [r for r in rows if r[1] not in range(1, 10)] + [("x: last task end (max warp)", 15), ("x: after flush (max warp)", 22), ("x: hot task 0 start", 16), ("x: hot task 0 end", 17),
+                 ("x: first cold task start", 18), ("x: first cold task end", 19), ("x: last cold task start", 20), ("x: last cold task end", 21)]
     for name, i in rows:
         x = us(tl[:, i])
         print(f"   {name:16s} min {x.min():8.1f}  mean {x.mean():8.1f}  max {x.max():8.1f} us")

@@ -9,7 +9,7 @@
 namespace v2e {
 
 constexpr int kMaxPartials = 2048;
-constexpr size_t kTimelineBytes = 160 * 32 * 8 + 2048;  // development aid: [cta][32] clock stamps + [128][2] launch start/end ring
+constexpr size_t kTimelineBytes = 160 * 32 * 8 + 2048 + 1024;  // development aid: [cta][32] clock stamps + [128][2] launch start/end ring + [128] rounds
 // fixed-point engine: ring of launch records for multi-sequence launches (8 slots x 16 sequences
 // x (SeqDev + 32 FrameSc) <= 8 * 16 * 1280 bytes)
 constexpr size_t kFxBlkBytes = 8 * 16 * 1280;

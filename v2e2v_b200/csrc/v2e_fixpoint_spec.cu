@@ -149,11 +149,44 @@ __device__ __forceinline__ void sp_stream_px(SpPx<NOISE>& o, const float (&x)[kS
     }
 }
 
-struct SpAcc {   // per-lane accumulators of a resolve round
-    unsigned nnz, nev;
-    long long s1;
-    unsigned long long lo, hi;
+// What the iteration loop (v2e_model.py:449-475) does to one pixel-frame, for the usual outcomes -
+// no event or exactly one - without walking it.  Iteration j of [0,c) carries an event; with the
+// gate on (:469) it is accepted iff ts_j - timestamp_mem > Tr (:419,:470), monotone in j.
+// Straight-line code:
+//   one  - exactly one event, at ts (iteration 0 when `first`)
+//   slow - anything else that is not "no event"
+struct SpEv1 {
+    bool one, slow, first;
+    float ts;
 };
+__device__ __forceinline__ SpEv1 sp_classify(const SpFrameEv& ev, bool gate, float cntf, bool bit,
+                                             float tm, float Tr) {
+    const float cf = fminf(cntf, ev.mxf);
+    const float tc = fadd(ev.t0, fmul(ev.step, cf));        // stamp of iteration c-1
+    const bool first = !gate || fsub(ev.ts1, tm) > Tr;      // iteration 0 passes
+    // else the first iteration that can pass, from an estimate: iteration j passes iff
+    // step * (j + 1) > Tr + timestamp_mem - t0 =: X, so the first one is floor(X / step).
+    // X / step sits next to an integer whenever the maxima of consecutive frames are commensurable
+    // (the usual case), so two neighbours are tried, each with the exact predicate.
+    float jl = floorf((Tr + tm - ev.t0) * ev.rstep - 0.5f);
+    jl = fmaxf(fminf(jl, cf - 1.f), 1.f);
+    const float tsa = fadd(ev.t0, fmul(ev.step, jl));         // iteration jl-1
+    const float tsb = fadd(ev.t0, fmul(ev.step, jl + 1.f));   // iteration jl
+    const float tsc = fadd(ev.t0, fmul(ev.step, jl + 2.f));   // iteration jl+1
+    const bool pb = fsub(tsb, tm) > Tr;
+    const bool any = cf >= 1.f && (!gate || fsub(tc, tm) > Tr);
+    const bool est = cf >= 2.f && !(fsub(tsa, tm) > Tr) &&
+                     (pb || (jl + 2.f <= cf && fsub(tsc, tm) > Tr));
+    SpEv1 r;
+    r.first = first;
+    r.ts = first ? ev.ts1 : (pb ? tsb : tsc);
+    const float nxt = first ? 1.f : (pb ? jl + 1.f : jl + 2.f);   // iterations consumed
+    // one more after it?  (gate off: every iteration is an event)
+    const bool more = nxt < cf && (!gate || fsub(tc, r.ts) > Tr);
+    r.slow = bit || (any && ((!first && !est) || more));
+    r.one = any && !r.slow;
+    return r;
+}
 
 template <int FDT, int R, int NOISE, bool CUTOFF>
 __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_constant__ FxParams prm) {
@@ -249,8 +282,9 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             kmax = fmaxf(kmax, fmaxf(s_fr[n].kp, s_fr[n].kn));
         }
         s_stat[3] = (float)max(2, gmin / 2);   // theta of the "hot" test
-        // 1024 * bound <= kmax4 * C: fx_shot_thr with its intensity factor (<= 1) dropped
-        s_stat[2] = kmax * 4.0f;
+        // 1024 * bound <= kmax4 * C: fx_shot_thr with its intensity factor 1 + m1 * inten01,
+        // inten01 in (0, 1], replaced by its largest value
+        s_stat[2] = kmax * 4.0f * (1.0f + fmaxf(cfg.shot_inten_m1, 0.f));
     }
     __syncthreads();
     const float theta = s_stat[3];
@@ -330,7 +364,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 }
                 unsigned* e = s_ent + slot;
                 // first active frame 0: found by the post pass
-                e[FX_META * cap] = (o.tm == 0.f ? 32u : 0u) | (cm << 6);
+                e[FX_META * cap] = (o.tm == 0.f ? 32u : 0u) | (cm << 6) | (o.allcand ? 0x20000u : 0u);
                 e[FX_IDX * cap] = (unsigned)(l + j);
                 e[FX_BASE * cap] = __float_as_uint(o.base0);
                 e[FX_POS * cap] = __float_as_uint(j ? pos2.y : pos2.x);
@@ -390,9 +424,24 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     // usually decide the per-frame maxima (pre-pass below).
     for (int i = tid; i < n_ent; i += kFxThreads) {
         unsigned* ep = s_ent + i;
-        const unsigned meta = ep[FX_META * cap];
-        const unsigned cm = (meta >> 6) & 0x3ffu;
+        unsigned meta = ep[FX_META * cap];
+        unsigned cm = (meta >> 6) & 0x3ffu;
         const float pos = __uint_as_float(ep[FX_POS * cap]), neg = __uint_as_float(ep[FX_NEG * cap]);
+        if (SHOT && cm != 0u && !(meta & 0x20000u)) {
+            // second stage of the shot test against the same upper bound: a marked frame has
+            // field 0, so its uniform is u2 / 1024 with u2 the draw the exact test will use
+            // (fx_event_frame); four marks in five go away here, one lane per entry, instead of
+            // costing a resolve task an out-of-line call every round
+            const int p = tile_px0 + (int)ep[FX_IDX * cap];
+            const float cmax = fmaxf(pos, neg);
+            for (int k = 0; k < kSpNF; ++k) {
+                if (!((cm >> k) & 1u)) continue;
+                const float tmax = (fmaxf(s_fr[k + 1].kp, s_fr[k + 1].kn) * 4.0f *
+                                    (1.0f + fmaxf(cfg.shot_inten_m1, 0.f))) * cmax;
+                if (!(fx_shot_uniform<R>(sq.philox_ctr, k + 1, p, 0u) * 1024.0f < tmax)) cm &= ~(1u << k);
+            }
+            meta = (meta & ~(0x3ffu << 6)) | (cm << 6);
+        }
         float base = __uint_as_float(ep[FX_BASE * cap]);
         const float base0 = base;
         int f = 0;
@@ -447,8 +496,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     bool converged = false;
     for (; pass < T + 3; ++pass) {
         const bool pre = pass == 0;
-        SpAcc acc;
-        acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
+        unsigned round_nev = 0;
         if (pre) {
             // The pre-pass only has to produce a good guess, and every warp of the grid waits for
             // its dependent chain of frames: one hot entry per lane, straight-line code, no voxel
@@ -524,6 +572,14 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                     on = i < n_cold;
                     e = s_perm[on ? i : 0];
                 }
+#ifdef SP_EXP_STAMPS
+                if (tl && pass == 1 && lane == 0) {
+                    const long long now = fx_now();
+                    if (t == 0) tl[16] = now;
+                    if (t == th) tl[18] = now;
+                    if (t == th + tc - 1) tl[20] = now;
+                }
+#endif
                 unsigned* ep = s_ent + e;
                 const unsigned meta = ep[FX_META * cap];
                 const int p = tile_px0 + (int)ep[FX_IDX * cap];
@@ -538,99 +594,144 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 unsigned nev = 0;
                 const int n_first = __reduce_min_sync(0xffffffffu, f);
                 const unsigned* nwp = ep + (nw_off + n_first - 1) * cap;
+                const bool has_cm = SHOT && __any_sync(0xffffffffu, cm != 0u);
+                // shot candidates, several events in one frame, estimate off: the generic code
+                // (out of line), accumulators via the entry's voxel words.  A macro, not a lambda:
+                // a closure that is not inlined would pin base, tm and the accumulators to local
+                // memory for the whole loop.
+#define SP_SLOW_FRAME(n_, cntf_, up_, C_, bit_)                                                        \
+    do {                                                                                               \
+        float* vp_ = (float*)(ep + FX_V0 * cap);                                                       \
+        vp_[0] = v0; vp_[cap] = v1; vp_[2 * cap] = v2; vp_[3 * cap] = v3; vp_[4 * cap] = v4;           \
+        const unsigned long long r_ = fx_event_frame<FDT, R, false>(                                   \
+            prm, sq, sm, (n_), p, (int)(cntf_), (up_) ? 1.f : -1.f, (C_), (bit_), SHOT, NOISE == 1, tm, \
+            vp_, cap);                                                                                 \
+        const int fin_ = (int)(r_ >> 32);                                                              \
+        tm = __uint_as_float((unsigned)r_);                                                            \
+        v0 = vp_[0]; v1 = vp_[cap]; v2 = vp_[2 * cap]; v3 = vp_[3 * cap]; v4 = vp_[4 * cap];           \
+        if (fin_) base = fadd(base, fmul(fmul((up_) ? 1.f : -1.f, (float)fin_), (C_))); /* :522 */     \
+        nev += (unsigned)fin_;                                                                         \
+    } while (0)
+                if (t < th) {
+                    // ---- hot entries: an event in most frames, the chain every round waits for;
+                    // straight-line code for every lane, predicated updates
 #pragma unroll 1
-                for (int n = n_first; n < T; ++n, nwp += cap) {
-#ifdef SP_EXP_STAMPS
-                    if (tl && pass == 0 && t == 0 && lane == 0) tl[13 + n] = fx_now();
-#endif
-                    const bool act = n >= f;
-                    const float b = LEAK ? fsub(base, __uint_as_float(nwp[kSpNF * cap])) : base;
-                    const float diff = fsub(__uint_as_float(nwp[0]), b);
-                    const float ad = fabsf(diff);
-                    const bool up = diff > 0.f;
-                    const float den = up ? denp : denn;
-                    const bool cross = act && ad >= den;   // den > 1e-6: the tolerance mask (:394) holds
-                    const bool bit = SHOT && act && ((cm >> (n - 1)) & 1u) && ad > 1e-6f;
-                    if (act) base = b;
-                    if (!__any_sync(0xffffffffu, cross || bit)) continue;   // a quiet frame for the whole task
-                    // event_counts (:404): 1 below twice the denominator (exact), else the quotient
-                    // (warp-uniform branch: cold tasks hardly ever divide)
-                    const bool big = cross && !(ad < fadd(den, den));
-                    float cntf = cross ? 1.f : 0.f;
-                    if (__any_sync(0xffffffffu, big)) {
-                        if (big) cntf = floorf(fdiv(ad, den));
-                    }
-                    const unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)(int)cntf);
-                    if (wmax > s_max[n] && lane == 0) atomicMax(&s_max[n], wmax);
-                    if (cross || bit) {
+                    for (int n = n_first; n < T; ++n, nwp += cap) {
+                        const bool act = n >= f;
                         const SpFrameEv ev = s_ev[n];
                         const bool gate = s_g[n].gate != 0;
+                        const float b = LEAK ? fsub(base, __uint_as_float(nwp[kSpNF * cap])) : base;
+                        const float diff = fsub(__uint_as_float(nwp[0]), b);
+                        const float ad = fabsf(diff);
+                        const bool up = diff > 0.f;
+                        const float den = up ? denp : denn;
+                        const bool cross = act && ad >= den;   // den > 1e-6: the tolerance mask (:394) holds
+                        const bool bit = has_cm && act && ((cm >> (n - 1)) & 1u) && ad > 1e-6f;
+                        if (act) base = b;
+                        const float cntf = cross ? floorf(fdiv(ad, den)) : 0.f;   // event_counts (:404)
+                        const unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)(int)cntf);
+                        if (wmax > s_max[n] && lane == 0) atomicMax(&s_max[n], wmax);
                         const float C = up ? pos : neg;
-                        // What the iteration loop (v2e_model.py:449-475) does to this pixel, for the
-                        // usual outcomes - no event or exactly one - without walking it.  Iteration
-                        // j of [0,c) carries an event; with the gate on (:469) it is accepted iff
-                        // ts_j - timestamp_mem > Tr (:419,:470), monotone in j.
-                        const float cf = fminf(cntf, ev.mxf);
-                        const float tc = fadd(ev.t0, fmul(ev.step, cf));        // stamp of iteration c-1
-                        const bool first = !gate || fsub(ev.ts1, tm) > Tr;      // iteration 0 passes
-                        // else the first iteration that can pass, from an estimate: iteration j
-                        // passes iff step * (j + 1) > Tr + timestamp_mem - t0 =: X, so the first
-                        // one is floor(X / step).  X / step sits next to an integer whenever the
-                        // maxima of consecutive frames are commensurable (the usual case), so two
-                        // neighbours are tried, each with the exact predicate.
-                        float jl = floorf((Tr + tm - ev.t0) * ev.rstep - 0.5f);
-                        jl = fmaxf(fminf(jl, cf - 1.f), 1.f);
-                        const float tsa = fadd(ev.t0, fmul(ev.step, jl));         // iteration jl-1
-                        const float tsb = fadd(ev.t0, fmul(ev.step, jl + 1.f));   // iteration jl
-                        const float tsc = fadd(ev.t0, fmul(ev.step, jl + 2.f));   // iteration jl+1
-                        const bool pb = fsub(tsb, tm) > Tr;
-                        const bool any = cf >= 1.f && (!gate || fsub(tc, tm) > Tr);
-                        const bool est = cf >= 2.f && !(fsub(tsa, tm) > Tr) &&
-                                         (pb || (jl + 2.f <= cf && fsub(tsc, tm) > Tr));
-                        const float ts = first ? ev.ts1 : (pb ? tsb : tsc);
-                        const float nxt = first ? 1.f : (pb ? jl + 1.f : jl + 2.f);   // iterations consumed
-                        // one more after it?  (gate off: every iteration is an event)
-                        const bool more = nxt < cf && (!gate || fsub(tc, ts) > Tr);
-                        int fin = 0;
-                        if (bit || (any && ((!first && !est) || more))) {
-                            // shot candidates, several events in the frame, estimate off: the
-                            // generic code, accumulators via the entry's voxel words
-#ifdef SP_EXP_STAMPS
-                            if (tl && pass == 0)
-                                atomicAdd((unsigned long long*)&tl[24], bit ? 1ull : more ? (1ull << 16) : (1ull << 32));
-#endif
-                            float* vp = (float*)(ep + FX_V0 * cap);
-                            vp[0] = v0; vp[cap] = v1; vp[2 * cap] = v2; vp[3 * cap] = v3; vp[4 * cap] = v4;
-                            const unsigned long long r = fx_event_frame<FDT, R, false>(
-                                prm, sq, sm, n, p, (int)cntf, up ? 1.f : -1.f, C, bit, SHOT, NOISE == 1, tm,
-                                vp, cap);
-                            fin = (int)(r >> 32);
-                            tm = __uint_as_float((unsigned)r);
-                            v0 = vp[0]; v1 = vp[cap]; v2 = vp[2 * cap]; v3 = vp[3 * cap]; v4 = vp[4 * cap];
-                            if (fin) base = fadd(base, fmul(fmul(up ? 1.f : -1.f, (float)fin), C));   // :522
-                        } else if (any) {
-                            // exactly one event, at ts (:478-502); pol * w is w or -w
-                            fin = 1;
-                            if (gate) tm = ts;
-                            float bbf = ev.bbf, wl = ev.wl, wr = ev.wr;
-                            if (!first) {
-                                bbf = floorf(ts);
-                                wr = fsub(ts, bbf);
-                                wl = fsub(1.0f, wr);
-                            }
-                            if (!up) { wl = -wl; wr = -wr; }
-                            if (bbf == 0.f) { v0 = fadd(v0, wl); v1 = fadd(v1, wr); }
-                            else if (bbf == 1.f) { v1 = fadd(v1, wl); v2 = fadd(v2, wr); }
-                            else if (bbf == 2.f) { v2 = fadd(v2, wl); v3 = fadd(v3, wr); }
-                            else if (bbf == 3.f) { v3 = fadd(v3, wl); v4 = fadd(v4, wr); }
-                            else if (bbf == 4.f) { v4 = fadd(v4, wl); }
-                            base = fadd(base, up ? C : -C);   // :522: (pol * 1) * C
+                        const SpEv1 r = sp_classify(ev, gate, cntf, bit, tm, Tr);
+                        if (__any_sync(0xffffffffu, r.slow)) {
+                            if (r.slow) SP_SLOW_FRAME(n, cntf, up, C, bit);
                         }
-                        nev += (unsigned)fin;
+                        // exactly one event, at ts (:478-502); pol * w is w or -w
+                        const float bbf = r.first ? ev.bbf : floorf(r.ts);
+                        float wr = r.first ? ev.wr : fsub(r.ts, bbf);
+                        float wl = r.first ? ev.wl : fsub(1.0f, wr);
+                        if (!up) { wl = -wl; wr = -wr; }
+                        if (r.one && bbf == 0.f) v0 = fadd(v0, wl);
+                        if (r.one && bbf == 1.f) v1 = fadd(v1, wl);
+                        if (r.one && bbf == 2.f) v2 = fadd(v2, wl);
+                        if (r.one && bbf == 3.f) v3 = fadd(v3, wl);
+                        if (r.one && bbf == 4.f) v4 = fadd(v4, wl);
+                        if (r.one && bbf == 0.f) v1 = fadd(v1, wr);
+                        if (r.one && bbf == 1.f) v2 = fadd(v2, wr);
+                        if (r.one && bbf == 2.f) v3 = fadd(v3, wr);
+                        if (r.one && bbf == 3.f) v4 = fadd(v4, wr);
+                        if (r.one) {
+                            if (gate) tm = r.ts;
+                            base = fadd(base, up ? C : -C);   // :522: (pol * 1) * C
+                            nev += 1u;
+                        }
+                    }
+                } else {
+                    // ---- cold entries: a few events per entry, most frames quiet.  Event-driven:
+                    // every lane scans its own frames to its next crossing (a handful of
+                    // instructions per frame), then the lanes that found one handle it together,
+                    // each at its own frame - a warp pays the event code once per event of its
+                    // busiest entry instead of once per frame.
+                    int n = f;   // this lane's frame cursor (>= T: nothing left)
+                    const unsigned* nwq = ep + (nw_off - 1) * cap;   // [n * cap]: frame n
+                    while (true) {
+                        float ad = 0.f, den = 1.f;
+                        bool up = false, bit = false;
+                        while (n < T) {
+                            const float b = LEAK ? fsub(base, __uint_as_float(nwq[(n + kSpNF) * cap])) : base;
+                            const float diff = fsub(__uint_as_float(nwq[n * cap]), b);
+                            ad = fabsf(diff);
+                            up = diff > 0.f;
+                            den = up ? denp : denn;
+                            base = b;
+                            bit = has_cm && ((cm >> (n - 1)) & 1u) && ad > 1e-6f;
+                            if (ad >= den || bit) break;   // den > 1e-6: the tolerance mask (:394) holds
+                            ++n;
+                        }
+                        if (!__any_sync(0xffffffffu, n < T)) break;
+                        if (n < T) {
+                            const bool cross = ad >= den;
+                            // event_counts (:404): 1 below twice the denominator (exact), else the quotient
+                            const bool big = cross && !(ad < fadd(den, den));
+                            float cntf = cross ? 1.f : 0.f;
+                            if (big) cntf = floorf(fdiv(ad, den));
+                            if ((unsigned)(int)cntf > s_max[n]) atomicMax(&s_max[n], (unsigned)(int)cntf);
+                            const SpFrameEv ev = s_ev[n];
+                            const bool gate = s_g[n].gate != 0;
+                            const float C = up ? pos : neg;
+                            // iteration 0 passes and none after it does (with the gate on nothing
+                            // passes within Tr of it: the last iteration, c-1, decides)
+                            bool simple = !bit && ev.mxf >= 1.f;
+                            if (gate) {
+                                simple = simple && fsub(ev.ts1, tm) > Tr;
+                                if (big) {
+                                    const float tc = fadd(ev.t0, fmul(ev.step, fminf(cntf, ev.mxf)));
+                                    simple = simple && !(fsub(tc, ev.ts1) > Tr);
+                                }
+                            } else {
+                                simple = simple && !big;
+                            }
+                            SpEv1 r;
+                            r.one = simple; r.slow = false; r.first = true; r.ts = ev.ts1;
+                            if (!simple) r = sp_classify(ev, gate, cntf, bit, tm, Tr);
+                            if (r.slow) {
+                                SP_SLOW_FRAME(n, cntf, up, C, bit);
+                            } else if (r.one) {
+                                // exactly one event, at ts (:478-502); pol * w is w or -w
+                                if (gate) tm = r.ts;
+                                const float bbf = r.first ? ev.bbf : floorf(r.ts);
+                                float wr = r.first ? ev.wr : fsub(r.ts, bbf);
+                                float wl = r.first ? ev.wl : fsub(1.0f, wr);
+                                if (!up) { wl = -wl; wr = -wr; }
+                                if (bbf == 0.f) { v0 = fadd(v0, wl); v1 = fadd(v1, wr); }
+                                else if (bbf == 1.f) { v1 = fadd(v1, wl); v2 = fadd(v2, wr); }
+                                else if (bbf == 2.f) { v2 = fadd(v2, wl); v3 = fadd(v3, wr); }
+                                else if (bbf == 3.f) { v3 = fadd(v3, wl); v4 = fadd(v4, wr); }
+                                else if (bbf == 4.f) { v4 = fadd(v4, wl); }
+                                base = fadd(base, up ? C : -C);   // :522: (pol * 1) * C
+                                nev += 1u;
+                            }
+                            ++n;
+                        }
                     }
                 }
 #ifdef SP_EXP_STAMPS
-                if (tl && pass == 0 && t == 0 && lane == 0) tl[23] = fx_now();
+                if (tl && pass == 1 && lane == 0) {
+                    const long long now = fx_now();
+                    if (t == 0) tl[17] = now;
+                    if (t == th) tl[19] = now;
+                    if (t == th + tc - 1) tl[21] = now;
+                }
 #endif
                 if (on) {
                     ep[FX_OB * cap] = __float_as_uint(base);
@@ -640,17 +741,26 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                     ep[(FX_V0 + 2) * cap] = __float_as_uint(v2);
                     ep[(FX_V0 + 3) * cap] = __float_as_uint(v3);
                     ep[(FX_V0 + 4) * cap] = __float_as_uint(v4);
-                    acc.nev += nev;
-                    fx_stat(v0, acc.nnz, acc.s1, acc.lo, acc.hi);
-                    fx_stat(v1, acc.nnz, acc.s1, acc.lo, acc.hi);
-                    fx_stat(v2, acc.nnz, acc.s1, acc.lo, acc.hi);
-                    fx_stat(v3, acc.nnz, acc.s1, acc.lo, acc.hi);
-                    fx_stat(v4, acc.nnz, acc.s1, acc.lo, acc.hi);
+                    round_nev += nev;
                 }
             }
+#ifdef SP_EXP_STAMPS
+            if (tl && pass == 1 && lane == 0) atomicMax((unsigned long long*)&tl[15], (unsigned long long)fx_now());
+#endif
+            // statistics of the voxel columns: a sweep of their own over the table (exact integers,
+            // order-free), so that the task loops above do not carry the accumulators
+            __syncthreads();
             FxAcc a;
-            a.nnz = acc.nnz; a.nev = acc.nev; a.s1 = acc.s1; a.lo = acc.lo; a.hi = acc.hi;
+            a.nnz = 0; a.nev = round_nev; a.s1 = 0; a.lo = 0; a.hi = 0;
+            for (int i = tid; i < n_ent; i += kFxThreads) {
+#pragma unroll
+                for (int b = 0; b < nb; ++b)
+                    fx_stat(__uint_as_float(s_ent[(FX_V0 + b) * cap + i]), a.nnz, a.s1, a.lo, a.hi);
+            }
             fx_flush(a, s_acc);
+#ifdef SP_EXP_STAMPS
+            if (tl && pass == 1 && lane == 0) atomicMax((unsigned long long*)&tl[22], (unsigned long long)fx_now());
+#endif
         }
         if (n_spill && !pre)
             fx_resolve_spill<FDT, R, false, true>(prm, sq, sm, spill_list, n_spill, tile_px0, spill_vox,
@@ -801,6 +911,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             fx.arrive = 0;
             if (prm.timeline && seq == 0) {
                 prm.timeline[160 * 32 + 2 * (fx.pad[0] & 127u) + 1] = fx_now();
+                prm.timeline[160 * 32 + 256 + (fx.pad[0] & 127u)] = pass + 1;   // rounds, pre-pass included
                 fx.pad[0] += 1;
             }
         }

@@ -382,9 +382,6 @@ class EventEmulator(nn.Module):
         out = torch.empty((K, self.num_bins, height, width), dtype=self.voxel_dtype, device=dev)
         meta = torch.zeros((K, 4), dtype=torch.int32, device=dev)   # num_events (i64), status, pad
         ostride = out.stride(0) * out.element_size()
-        for k in range(K):
-            self._prep_pack(packs[k], frames[k], t_frames[k], out.data_ptr() + k * ostride,
-                            meta.data_ptr() + 16 * k)
         evp = None
         if events is not None:
             if len(events) != 2 * K:
@@ -393,10 +390,25 @@ class EventEmulator(nn.Module):
             for i, e in enumerate(events):
                 e.record()                      # forces creation of the cudaEvent_t
                 evp[i] = e.cuda_event
-        rc = pl._lib.v2e_clip_forward(C.byref(pl.cfg), packs, K, self._workspace.data_ptr(),
-                                      self._workspace.numel(),
-                                      torch.cuda.current_stream(dev).cuda_stream, evp)
-        _cabi.check(rc, "v2e_clip_forward")
+        # The host-side preparation of a pack (stamps -> scalars, the torch expressions of
+        # v2e_model.py:303-318) costs about half a kernel: packs are prepared and enqueued in
+        # growing chunks, so that the device works on chunk i while the host prepares chunk i+1.
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        out_ptr, meta_ptr = out.data_ptr(), meta.data_ptr()
+        k0, chunk = 0, 1
+        while k0 < K:
+            k1 = min(K, k0 + chunk)
+            for k in range(k0, k1):
+                self._prep_pack(packs[k], frames[k], t_frames[k], out_ptr + k * ostride,
+                                meta_ptr + 16 * k)
+            pk0 = C.cast(C.addressof(packs) + k0 * C.sizeof(_cabi.Pack), C.POINTER(_cabi.Pack))
+            ev0 = None
+            if evp is not None:
+                ev0 = C.cast(C.addressof(evp) + 2 * k0 * C.sizeof(C.c_void_p), C.POINTER(C.c_void_p))
+            rc = pl._lib.v2e_clip_forward(C.byref(pl.cfg), pk0, k1 - k0, self._workspace.data_ptr(),
+                                          self._workspace.numel(), stream, ev0)
+            _cabi.check(rc, "v2e_clip_forward")
+            k0, chunk = k1, min(2 * chunk, 16)
         self._clip_keep = (frames, packs)       # keep the inputs alive until the stream is done
         self._last_meta = meta[-1]
         self._clip_meta = meta
