@@ -283,6 +283,108 @@ def test_fixpoint_other_pack_shapes(T, nb, vdt):
     assert em.resolved_engine == "fixpoint"
 
 
+def _run_fixpoint(cfg, noise, debug, fdt, vids, planes, seed=4242):
+    em = gc.cuda_emulator(cfg, "fixpoint", noise_mode=noise, debug_maps=debug)
+    em.philox_seed = seed
+    em.set_planes(*planes)
+    out = []
+    for fr, tfr in vids:
+        ev, nev = em(fr.to("cuda").to(fdt), tfr)
+        out.append((ev.cpu().numpy().copy(), nev, em.base_log_frame.cpu().numpy().copy(),
+                    em.lp_log_frame0.cpu().numpy().copy() if cfg["cutoff_hz"] > 0 else None,
+                    em.timestamp_mem.cpu().numpy().copy()))
+    return out
+
+
+@pytest.mark.parametrize("noise", ["philox", "off"])
+@pytest.mark.parametrize("cfgname,H,W,fdt", [
+    ("CFG2", 96, 128, torch.float32),
+    ("CFG2", 260, 346, torch.uint8),       # configs[3] geometry, W % 4 != 0
+    ("CFG2", 180, 240, torch.bfloat16),    # configs[1]
+    ("CFG1", 180, 240, torch.float32),     # configs[0] parameters (no cutoff, no diversity)
+])
+def test_specialised_kernel_equals_generic(noise, cfgname, H, W, fdt):
+    """The kernel specialised for the reference pack shape (what serves every call without debug
+    maps: v2e_fixpoint_spec.cu) against the generic kernel (debug maps on, the one the oracle
+    tests above pin): same seed, same video => bit-identical states, counts and voxel grids."""
+    cfg = dict(getattr(gc, cfgname))
+    if noise == "off":
+        cfg.update(leak_rate_hz=0, shot_noise_rate_hz=0)
+    planes = gc.make_planes(5, H, W, cfg)
+    vids = [(fr, tfr) for _, fr, tfr in gc.video(3, 4, 10, H, W)]
+    a = _run_fixpoint(cfg, noise, True, fdt, vids, planes)
+    b = _run_fixpoint(cfg, noise, False, fdt, vids, planes)
+    for k, (x, y) in enumerate(zip(a, b)):
+        assert x[1] == y[1], f"num_events pack {k}"
+        np.testing.assert_array_equal(x[2], y[2], err_msg=f"base pack {k}")
+        if x[3] is not None:
+            np.testing.assert_array_equal(x[3], y[3], err_msg=f"lp pack {k}")
+        np.testing.assert_array_equal(x[4], y[4], err_msg=f"tmem pack {k}")
+        np.testing.assert_array_equal(x[0], y[0], err_msg=f"voxel pack {k}")
+
+
+@pytest.mark.parametrize("fps,sigma", [(100.0, 6.0), (30.0, 12.0), (1000.0, 25.0)])
+def test_specialised_kernel_other_regimes_vs_oracle(fps, sigma):
+    """Regimes away from the 1000 fps knife edge (SURVEY trap T9): at 100 / 30 fps the refractory
+    gate (v2e_model.py:469) is off for most frames and a pixel emits every event it counts; at
+    sigma 25 pixels cross several thresholds per frame.  Specialised kernel (no debug maps) vs the
+    oracle, noise off: states and counts bit-exact."""
+    cfg = dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0)
+    H, W, T = 120, 160, 10
+    pos, neg, _ = gc.make_planes(9, H, W, cfg)
+    em = gc.cuda_emulator(cfg, "fixpoint")
+    orc = OracleEmulator(**cfg, threads=0)
+    em.set_planes(pos, neg)
+    orc.set_planes(pos, neg)
+    for k, fr, tfr in gc.video(6, 3, T, H, W, fps=fps, sigma=sigma):
+        ev, nev = em(fr.cuda(), tfr)
+        ov, onev = orc.forward(fr.numpy(), tfr)
+        assert nev == onev, f"pack {k}"
+        gc.assert_state_equal(em, orc, True, f"pack {k}")
+        np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+
+
+def test_fixpoint_odd_width_takes_generic_kernel():
+    """An odd width (pixel pairs would straddle rows) is served by the generic kernel: same
+    results as the oracle."""
+    cfg = dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0)
+    H, W, T = 33, 47, 10
+    pos, neg, _ = gc.make_planes(3, H, W, cfg)
+    em = gc.cuda_emulator(cfg, "fixpoint")
+    orc = OracleEmulator(**cfg)
+    em.set_planes(pos, neg)
+    orc.set_planes(pos, neg)
+    for k, fr, tfr in gc.video(2, 3, T, H, W):
+        ev, nev = em(fr.cuda(), tfr)
+        ov, onev = orc.forward(fr.numpy(), tfr)
+        assert nev == onev, f"pack {k}"
+        gc.assert_state_equal(em, orc, True, f"pack {k}")
+        np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+
+
+def test_specialised_kernel_table_overflow_spills():
+    """More active pixels in a tile than its table holds (a flickering image): the overflow
+    takes the spill path, results still match the oracle."""
+    cfg = dict(gc.CFG1, leak_rate_hz=0, shot_noise_rate_hz=0)
+    H, W, T = 720, 1280, 10     # 6 227 pixels per tile on 148 SMs, nearly all of them active
+    pos, neg, _ = gc.make_planes(4, H, W, cfg)
+    em = gc.cuda_emulator(cfg, "fixpoint")
+    orc = OracleEmulator(**cfg, threads=0)
+    em.set_planes(pos, neg)
+    orc.set_planes(pos, neg)
+    g = torch.Generator().manual_seed(1)
+    base = torch.randint(40, 200, (1, 1, H, W), generator=g).float()
+    for k in range(2):
+        flick = (torch.randint(0, 2, (1, T, H, W), generator=g).float() * 2 - 1) * 60
+        fr = (base + flick).clamp(0, 255).round()
+        tfr = gc.stamps(k, T, 1000.0)
+        ev, nev = em(fr.cuda(), tfr)
+        ov, onev = orc.forward(fr.numpy(), tfr)
+        assert nev == onev, f"pack {k}"
+        gc.assert_state_equal(em, orc, False, f"pack {k}")
+        np.testing.assert_allclose(ev.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+
+
 def test_time_order_error_and_reset():
     em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
     fr = torch.randint(0, 255, (1, 4, 16, 16)).float().cuda()

@@ -72,13 +72,18 @@ struct SpPx {   // one pixel after the frame loop
 
 // The frame loop of one pixel (v2e_model.py:321-322,332,350-404 up to the threshold test):
 // everything the frames present to the pixel whatever it does.
-template <int FDT, int R, int NOISE, bool CUTOFF>
+// ONE: a single-sequence launch, whose per-frame scalars sit in the kernel parameters: they become
+// constant-bank operands of the arithmetic instead of a shared-memory load each.
+// SMALL: the pixel sits on the sensing-diversity grid (even row and column), a compile-time
+// choice so that the scalar is an operand and not a select.
+template <int FDT, int R, int NOISE, bool CUTOFF, bool ONE, bool SMALL>
 __device__ __forceinline__ void sp_stream_px(SpPx<NOISE>& o, const float (&x)[kSpNF], float x0,
                                              float pos, float neg, float nra, float base_in,
-                                             float lp_in, float tm_in, bool small, unsigned p,
-                                             const CfgDev& cfg, const SeqDev& sq,
+                                             float lp_in, float tm_in, unsigned p,
+                                             const FxParams& prm, const SeqDev& sq,
                                              const float2* s_lut, const FrameSc* s_fr,
                                              float kmax4) {
+    const CfgDev& cfg = prm.cfg;
     bool bad = false;
     float base, lp, tm;
     if (sq.first_pack) {
@@ -110,11 +115,11 @@ __device__ __forceinline__ void sp_stream_px(SpPx<NOISE>& o, const float (&x)[kS
     float z0 = 0.f, z1 = 0.f;
 #pragma unroll
     for (int k = 0; k < kSpNF; ++k) {
-        const FrameSc& fs = s_fr[k + 1];
+        const FrameSc& fs = ONE ? prm.one.fr[k + 1] : s_fr[k + 1];
         const float2 li = s_lut[sp_index<FDT>(x[k], bad)];
         float nwk = li.x;
         if (CUTOFF) {
-            lp = lowpass(lp, li.x, li.y, small ? fs.s_small : fs.s_large);
+            lp = lowpass(lp, li.x, li.y, SMALL ? fs.s_small : fs.s_large);
             nwk = lp;
         }
         o.nw[k] = nwk;
@@ -188,7 +193,7 @@ __device__ __forceinline__ SpEv1 sp_classify(const SpFrameEv& ev, bool gate, flo
     return r;
 }
 
-template <int FDT, int R, int NOISE, bool CUTOFF>
+template <int FDT, int R, int NOISE, bool CUTOFF, bool ONE>
 __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_constant__ FxParams prm) {
     constexpr bool LEAK = NOISE == 1, SHOT = NOISE == 1;
     constexpr int T = kFxSpecT, nb = kFxSpecNb;
@@ -323,11 +328,17 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
 #pragma unroll
             for (int k = 0; k < kSpNF; ++k) x[k] = j ? x2[k].y : x2[k].x;
             SpPx<NOISE> o;
-            sp_stream_px<FDT, R, NOISE, CUTOFF>(o, x, j ? x02.y : x02.x, j ? pos2.y : pos2.x,
-                                                j ? neg2.y : neg2.x, j ? nra2.y : nra2.x,
-                                                j ? base2.y : base2.x, j ? lp2.y : lp2.x,
-                                                j ? tm2.y : tm2.x, j ? false : small0,
-                                                (unsigned)(p + j), cfg, sq, s_lut, s_fr, kmax4);
+            // (a row holds a whole number of warp chunks at the usual widths, so the branch on
+            // the first pixel's grid membership is warp-uniform)
+            if (j == 0 && CUTOFF && small0)
+                sp_stream_px<FDT, R, NOISE, CUTOFF, ONE, true>(o, x, x02.x, pos2.x, neg2.x, nra2.x, base2.x,
+                                                               lp2.x, tm2.x, (unsigned)p, prm, sq, s_lut,
+                                                               s_fr, kmax4);
+            else
+                sp_stream_px<FDT, R, NOISE, CUTOFF, ONE, false>(
+                    o, x, j ? x02.y : x02.x, j ? pos2.y : pos2.x, j ? neg2.y : neg2.x, j ? nra2.y : nra2.x,
+                    j ? base2.y : base2.x, j ? lp2.y : lp2.x, j ? tm2.y : tm2.x, (unsigned)(p + j), prm, sq,
+                    s_lut, s_fr, kmax4);
             // ---- quiet -> finished; maybe active -> table entry (or spill when the table is full)
             const bool want = valid && (o.act || o.cand) && !o.bad;
             const unsigned am = __ballot_sync(0xffffffffu, want);
@@ -919,10 +930,10 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-template <int FDT, int R, int NOISE, bool CUTOFF>
-static int launch_spec_v(const FxParams& prm, int grid, size_t smem, int optin, cudaStream_t st) {
+template <int FDT, int R, int NOISE, bool CUTOFF, bool ONE>
+static int launch_spec_1(const FxParams& prm, int grid, size_t smem, int optin, cudaStream_t st) {
     static bool attr_set = false;  // one process drives one device (multi-GPU)
-    auto kern = k_fixpoint_spec<FDT, R, NOISE, CUTOFF>;
+    auto kern = k_fixpoint_spec<FDT, R, NOISE, CUTOFF, ONE>;
     int rc = V2E_OK;
     if (!attr_set) {
         rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
@@ -934,6 +945,12 @@ static int launch_spec_v(const FxParams& prm, int grid, size_t smem, int optin, 
                                              args, smem, st));
     count_launch();
     return rc;
+}
+
+template <int FDT, int R, int NOISE, bool CUTOFF>
+static int launch_spec_v(const FxParams& prm, int grid, size_t smem, int optin, cudaStream_t st) {
+    return prm.blocks ? launch_spec_1<FDT, R, NOISE, CUTOFF, false>(prm, grid, smem, optin, st)
+                      : launch_spec_1<FDT, R, NOISE, CUTOFF, true>(prm, grid, smem, optin, st);
 }
 
 template <int FDT>
