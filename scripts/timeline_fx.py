@@ -31,14 +31,9 @@ for k, fr, tfr in gc.video(1, 5, T, H, W):
         rows += [(f"resolve{ps} done", 3 + 3 * ps)] + ([(f"arrived{ps}", 5 + 3 * ps)] if ps < 3 else []) + [(f"barrier{ps} done", 4 + 3 * ps)]
     rows += [("loop exit", 27), ("commit done", 31)]
     if os.environ.get("V2E_STAMPS"):
-        fr = tl[:, 1:10].astype(np.float64)
-        end = tl[:, 19].astype(np.float64)
-        ok = (fr > 0).all(axis=1) & (end > 0)
-        if ok.any():
-            d = np.diff(np.concatenate([fr[ok], end[ok, None]], axis=1), axis=1) / 1e3
-            print("   round 1, first cold task, per frame (us): " + " ".join(f"{x:.2f}" for x in d.mean(axis=0)) +
-                  f"   | non-simple event lanes/tile: general {(tl[:,24] & 0xffffffff).mean():.1f} slow {(tl[:,24] >> 32).mean():.1f}")
-        rows = [r for r in rows if r[1] not in range(1, 10)] + [("x: last task end (max warp)", 15), ("x: after flush (max warp)", 22), ("x: hot task 0 start", 16), ("x: hot task 0 end", 17),
+        c = tl[:, 24]
+        print(f"   first full round, cold event lanes per tile: slow(shot) {(c & 0xffff).mean():.1f} slow(other) {((c >> 16) & 0xffff).mean():.1f} classified {((c >> 32) & 0xffff).mean():.1f} simple {((c >> 48) & 0xffff).mean():.1f}")
+        rows += [("x: last task end (max warp)", 15), ("x: after flush (max warp)", 22), ("x: hot task 0 start", 16), ("x: hot task 0 end", 17),
                  ("x: first cold task start", 18), ("x: first cold task end", 19), ("x: last cold task start", 20), ("x: last cold task end", 21)]
     for name, i in rows:
         x = us(tl[:, i])

@@ -48,6 +48,10 @@ struct FxWork {
     unsigned guess[V2E_MAX_FRAMES];  // last pack's per-frame max event count + 1 (0: none yet)
     unsigned gmax[kFxMaxRounds][V2E_MAX_FRAMES];
     unsigned long long stat[kFxMaxRounds][8];
+    // pre-pass rounds of the specialised kernel: what they exchange is only a hint, so each tile
+    // publishes ONE self-validating 64-bit word (round tag | nine 6-bit saturated maxima) with a
+    // relaxed store and polls everybody else's: no atomics, no fences
+    unsigned long long hint[2][kRaMaxTiles];
 };
 
 struct StepLayout {

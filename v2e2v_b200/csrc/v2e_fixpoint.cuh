@@ -37,6 +37,8 @@ enum {
     FX_BASE,       // base_log_frame before frame f
     FX_POS, FX_NEG,
     FX_OB, FX_OT,  // results: base_log_frame, timestamp_mem
+    FX_SI, FX_SU,  // specialised kernel: an entry's one shot-candidate frame - inten01 of that
+                   // frame and the frame's uniform (post pass; valid when META says so)
     FX_V0          // results: num_bins voxel accumulators
 };
 
@@ -96,6 +98,9 @@ __device__ __forceinline__ unsigned long long fx_ld_relaxed64(const unsigned lon
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void fx_st_relaxed64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void fx_red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

@@ -28,6 +28,17 @@ constexpr int kSpNF = kFxSpecT - 1;   // frames 1..9 of the pack carry events
 #define V2E_SP_HOT_LANES 32
 #endif
 constexpr int kSpHotLanes = V2E_SP_HOT_LANES;   // entries per task of the hot list
+#ifndef V2E_SP_PRE
+#define V2E_SP_PRE 2
+#endif
+constexpr unsigned kSpStatic = 0x40000u, kSpStaticUp = 0x80000u;   // entry META flags (post pass)
+#ifndef V2E_SP_BUSY
+#define V2E_SP_BUSY 2
+#endif
+constexpr int kSpBusy = V2E_SP_BUSY;   // crossing frames after the first that make an entry "busy"
+constexpr unsigned kSpShotData = 0x100000u;   // FX_SI / FX_SU hold the entry's one marked frame
+constexpr int kSpPre = V2E_SP_PRE;   // pre-pass rounds (hot entries only) before the first full round
+static_assert(kSpPre >= 1 && kSpPre <= 2, "FxWork::hint holds two rounds");
 
 // Per-frame constants of the resolve loop, all derived from the frame's guessed maximum
 // (v2e_model.py:405-422,469): the time axis of the frame's iterations and what an event at the
@@ -231,6 +242,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     unsigned long long* s_tot = (unsigned long long*)(smem_raw + 3752);  // 5 * 8: sequence totals
     int* s_cnt = (int*)(smem_raw + 3792);   // [0] slot counter, [1] spilled, [2] error, [3] entries, [5] task counter
     float* s_stat = (float*)(smem_raw + 3824);                           // mean, den, on, theta
+    int* s_sc = (int*)(smem_raw + 2944);    // 2 x 16: single-event entries per frame, ON / OFF
     unsigned short* s_perm = (unsigned short*)(smem_raw + kFxPermOff);
     int* s_hist = (int*)(smem_raw + kFxPermOff + 2 * kFxPermMax);        // 2 x 64 ints
     unsigned* s_ent = (unsigned*)(smem_raw + kFxHeader);
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
     if (tid < 8) s_cnt[tid] = 0;
     if (tid < 128) s_hist[tid] = 0;
+    if (tid < 32) s_sc[tid] = 0;
     __syncthreads();
     if (tid == 0) {
         int gmin = 0x7fffffff;
@@ -429,10 +442,20 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     const int n_ent = s_cnt[3];
     const int n_spill = s_cnt[1];
     // ================================ post pass over the table =====================================
-    // first active frame f (exact test, v2e_model.py:394-404), brightness before it, "hot" flag:
-    // some frame is theta thresholds away from the brightness the entry starts with - a bound no
-    // event count of the pixel exceeds by much.  Scheduling hint only: the hot entries alone
-    // usually decide the per-frame maxima (pre-pass below).
+    // Per entry: first active frame f (exact test, v2e_model.py:394-404), brightness before it,
+    // "hot" flag (some frame is theta thresholds away from the brightness the entry starts with -
+    // a bound no event count of the pixel exceeds by much; a scheduling hint: the hot entries
+    // alone usually decide the per-frame maxima), and the STATIC entries, whose fate does not
+    // depend on the maxima at all:
+    //   * nothing happens (the stream test was conservative, or its shot marks went away);
+    //   * exactly one event: a single frame crosses, by one threshold, it is the pixel's first
+    //     event of the pack (timestamp_mem = -Tr: iteration 0 always passes the gate, and the
+    //     frame's maximum is >= 1 because this very pixel counts 1), and with the brightness
+    //     stepped by that event (:522) no later frame crosses.  Three entries in five.
+    // Only the event's time stamp - the frame's first, hence its voxel weights - depends on the
+    // guess, and it is the same for all of them: static entries never enter a resolve round;
+    // they are counted per frame and polarity, their statistics follow from the counts, and the
+    // commit writes their columns from the final frame constants.
     for (int i = tid; i < n_ent; i += kFxThreads) {
         unsigned* ep = s_ent + i;
         unsigned meta = ep[FX_META * cap];
@@ -452,33 +475,75 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 if (!(fx_shot_uniform<R>(sq.philox_ctr, k + 1, p, 0u) * 1024.0f < tmax)) cm &= ~(1u << k);
             }
             meta = (meta & ~(0x3ffu << 6)) | (cm << 6);
+            if (__popc(cm) == 1) {
+                // the usual survivor: one marked frame.  What its exact test needs besides the
+                // pixel's state - the frame's inten01 and uniform - is fetched once, here, instead
+                // of by an out-of-line call in every resolve round (emulator_utils.py:173-188)
+                const int k1 = __ffs((int)cm) - 1;
+                float L1, I1;
+                log_inten(s_lut, load_frame1<FDT>(sq.frames, (long long)(k1 + 1) * P + p), L1, I1);
+                ep[FX_SI * cap] = __float_as_uint(I1);
+                ep[FX_SU * cap] = __float_as_uint(fx_shot_uniform<R>(sq.philox_ctr, k1 + 1, p, 0u));
+                meta |= kSpShotData;
+            }
         }
         float base = __uint_as_float(ep[FX_BASE * cap]);
         const float base0 = base;
         int f = 0;
-        float sb = 0.f;
-        bool hot = false;
+        float sb = 0.f, bs = 0.f;
+        bool hot = false, one = false, more = false, up1 = false;
+        int ncross = 0;
 #pragma unroll
         for (int k = 0; k < kSpNF; ++k) {
             const float nw = __uint_as_float(ep[(nw_off + k) * cap]);
-            const float b = LEAK ? fsub(base, __uint_as_float(ep[(dl_off + k) * cap])) : base;
+            const float dlk = LEAK ? __uint_as_float(ep[(dl_off + k) * cap]) : 0.f;
+            const float b = LEAK ? fsub(base, dlk) : base;
             const float diff = fsub(nw, b);
             const float ad = fabsf(diff);
             const bool up = diff > 0.f;
             const float den = fadd(up ? pos : neg, 1e-9f);
             const bool hit = !f && ad > 1e-6f && (ad >= den || ((cm >> k) & 1u));
-            if (hit) { f = k + 1; sb = base; }
+            if (f) {
+                // after the first active frame: would anything else happen had it been one event?
+                // (and, as a scheduling hint, how many more frames cross if each gives one event)
+                const float b2 = LEAK ? fsub(bs, dlk) : bs;
+                const float d2 = fsub(nw, b2);
+                const bool x2 = fabsf(d2) >= fadd(d2 > 0.f ? pos : neg, 1e-9f);
+                more = more || x2;
+                ncross += x2 ? 1 : 0;
+                bs = x2 ? (d2 > 0.f ? fadd(b2, pos) : fadd(b2, -neg)) : b2;
+            }
+            if (hit) {
+                f = k + 1;
+                sb = base;
+                one = ad >= den && ad < fadd(den, den) && cm == 0u && !(meta & 32u);
+                up1 = up;
+                bs = up ? fadd(b, pos) : fadd(b, -neg);   // :522 with one event: base + pol * C
+            }
             const float d0 = fsub(nw, base0);
             hot = hot || fabsf(d0) >= theta * (d0 > 0.f ? pos : neg);
             if (!f) base = b;
         }
-        if (!f) { f = 31; sb = base; }   // nothing happens after all: the entry only carries its state
-        ep[FX_META * cap] = meta | (unsigned)f | (hot ? 0x10000u : 0u);
+        // busy entries (an event in four frames or more) join the hot list: its frame-synchronous
+        // straight-line loop beats the event-driven one when most frames hold an event
+        hot = hot || ncross >= kSpBusy;
+        const bool idle = !f;
+        if (idle) { f = 31; sb = base; bs = base; }   // nothing happens: the entry only carries its state
+        const bool stat = idle || (one && !more);
+        ep[FX_META * cap] = meta | (unsigned)f | (hot ? 0x10000u : 0u) | (stat ? kSpStatic : 0u) |
+                            (up1 ? kSpStaticUp : 0u);
         ep[FX_BASE * cap] = __float_as_uint(sb);
-        atomicAdd(&s_hist[(hot ? 32 : 0) + f], 1);
+        if (stat) {
+            ep[FX_OB * cap] = __float_as_uint(bs);
+#pragma unroll
+            for (int b = 0; b < nb; ++b) ep[(FX_V0 + b) * cap] = 0u;   // the statistics sweep reads these
+            if (!idle) atomicAdd(&s_sc[(up1 ? 0 : 16) + f], 1);
+        } else {
+            atomicAdd(&s_hist[(hot ? 32 : 0) + f], 1);
+        }
     }
     __syncthreads();
-    // ---- order the entries by first active frame (counting sort; order within a frame is free) ---
+    // ---- order the listed entries by first active frame (counting sort; order within a frame is free)
     if (tid == 0) {
         int o = 0;
         for (int i = 0; i < 64; ++i) {   // cold frames 0..31, then hot frames 0..31
@@ -487,11 +552,14 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             o += c;
             if (i == 31) s_cnt[4] = o;   // cold entries
         }
+        s_cnt[6] = o;                    // entries that take part in the resolve rounds
     }
+    if (tid >= 1 && tid < T) s_max[tid] = (s_sc[tid] + s_sc[16 + tid]) > 0 ? 1u : 0u;
     __syncthreads();
-    const int n_cold = s_cnt[4], n_hot = n_ent - n_cold;
+    const int n_cold = s_cnt[4], n_hot = s_cnt[6] - n_cold;
     for (int i = tid; i < n_ent; i += kFxThreads) {
         const unsigned meta = s_ent[FX_META * cap + i];
+        if (meta & kSpStatic) continue;
         s_perm[atomicAdd(&s_hist[64 + ((meta & 0x10000u) ? 32 : 0) + (int)(meta & 31u)], 1)] = (unsigned short)i;
     }
     __syncthreads();
@@ -505,9 +573,8 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     const float Tr = sq.Tr;
     int pass = 0;
     bool converged = false;
-    for (; pass < T + 3; ++pass) {
-        const bool pre = pass == 0;
-        unsigned round_nev = 0;
+    for (; pass < T + 3 + kSpPre; ++pass) {
+        const bool pre = pass < kSpPre;
         if (pre) {
             // The pre-pass only has to produce a good guess, and every warp of the grid waits for
             // its dependent chain of frames: one hot entry per lane, straight-line code, no voxel
@@ -524,23 +591,29 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 const float neg = __uint_as_float(ep[FX_NEG * cap]);
                 const float denp = fadd(pos, 1e-9f), denn = fadd(neg, 1e-9f);
                 const int f = on ? (int)(meta & 31u) : V2E_MAX_FRAMES;
-                const int n_first = __reduce_min_sync(0xffffffffu, f);
-                const unsigned* nwp = ep + (nw_off + n_first - 1) * cap;
-#pragma unroll 1
-                for (int n = n_first; n < T; ++n, nwp += cap) {
+                // fully unrolled: the table reads and the frame constants leave the chain
+                float nwv[kSpNF], dlv[kSpNF], cmax[kSpNF];
+#pragma unroll
+                for (int k = 0; k < kSpNF; ++k) {
+                    nwv[k] = __uint_as_float(ep[(nw_off + k) * cap]);
+                    dlv[k] = LEAK ? __uint_as_float(ep[(dl_off + k) * cap]) : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < kSpNF; ++k) {
+                    const int n = k + 1;
                     const bool act = n >= f;
                     const SpFrameEv ev = s_ev[n];
                     const bool gate = s_g[n].gate != 0;
-                    const float b = LEAK ? fsub(base, __uint_as_float(nwp[kSpNF * cap])) : base;
-                    const float diff = fsub(__uint_as_float(nwp[0]), b);
+                    const float b = LEAK ? fsub(base, dlv[k]) : base;
+                    const float diff = fsub(nwv[k], b);
                     const float ad = fabsf(diff);
                     const bool up = diff > 0.f;
                     const float den = up ? denp : denn;
                     const bool cross = act && ad >= den;
                     if (act) base = b;
-                    const float cntf = cross ? floorf(fdiv(ad, den)) : 0.f;   // event_counts (:404)
-                    const unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)(int)cntf);
-                    if (wmax > s_max[n] && lane == 0) atomicMax(&s_max[n], wmax);
+                    // event_counts (:404); an approximate quotient will do for a hint
+                    const float cntf = cross ? floorf(__fdividef(ad, den)) : 0.f;
+                    cmax[k] = cntf;
                     const float cf = fminf(cntf, ev.mxf);
                     const float tc = fadd(ev.t0, fmul(ev.step, cf));
                     const bool first = fsub(ev.ts1, tm) > Tr;
@@ -550,15 +623,19 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                     const float tsc = fadd(ev.t0, fmul(ev.step, jl + 2.f));
                     const float ts = first ? ev.ts1 : (fsub(tsb, tm) > Tr ? tsb : tsc);
                     const float C = up ? pos : neg;
-                    if (gate) {
-                        if (cf >= 1.f && fsub(tc, tm) > Tr) {
-                            tm = ts;
-                            base = fadd(base, up ? C : -C);
-                        }
-                    } else if (cf >= 1.f) {
-                        base = fadd(base, fmul(fmul(up ? 1.f : -1.f, cf), C));
-                    }
+                    const bool hit = cf >= 1.f && (!gate || fsub(tc, tm) > Tr);
+                    const float step_c = gate ? (up ? C : -C) : fmul(fmul(up ? 1.f : -1.f, cf), C);
+                    if (hit && gate) tm = ts;
+                    if (hit) base = fadd(base, step_c);
                 }
+                // the warp's maxima: nine reductions back to back, then lane k publishes frame k+1
+                unsigned mine = 0u;
+#pragma unroll
+                for (int k = 0; k < kSpNF; ++k) {
+                    const unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)(int)cmax[k]);
+                    if (lane == k) mine = wmax;
+                }
+                if (lane < kSpNF && mine) atomicMax(&s_max[lane + 1], mine);
             }
         } else {
             // tasks drawn from a queue: the hot list first (short tasks of kSpHotLanes entries:
@@ -584,7 +661,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                     e = s_perm[on ? i : 0];
                 }
 #ifdef SP_EXP_STAMPS
-                if (tl && pass == 1 && lane == 0) {
+                if (tl && pass == kSpPre && lane == 0) {
                     const long long now = fx_now();
                     if (t == 0) tl[16] = now;
                     if (t == th) tl[18] = now;
@@ -623,6 +700,25 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
         if (fin_) base = fadd(base, fmul(fmul((up_) ? 1.f : -1.f, (float)fin_), (C_))); /* :522 */     \
         nev += (unsigned)fin_;                                                                         \
     } while (0)
+                // a shot candidate whose inten01 and uniform are at hand: straight to the iteration
+                // loop (what fx_event_frame does once it has decided `cand`)
+#define SP_SHOT_FRAME(n_, cntf_, up_, C_, I_, u_)                                                       \
+    do {                                                                                               \
+        float* vp_ = (float*)(ep + FX_V0 * cap);                                                       \
+        vp_[0] = v0; vp_[cap] = v1; vp_[2 * cap] = v2; vp_[3 * cap] = v3; vp_[4 * cap] = v4;           \
+        const FrameGlobals g_ = s_g[(n_)];                                                             \
+        const unsigned long long r_ = fx_events<R>(                                                    \
+            &prm.cfg, &sq, &s_fr[(n_)], g_.mx, g_.ts_step, g_.gate, (n_), p, (up_) ? 1.f : -1.f, (C_), \
+            min((int)(cntf_), g_.mx), (I_), tm, g_.mx > 0 ? 2 : 0, (u_), vp_, cap);                    \
+        const int fin_ = (int)(r_ >> 32);                                                              \
+        tm = __uint_as_float((unsigned)r_);                                                            \
+        v0 = vp_[0]; v1 = vp_[cap]; v2 = vp_[2 * cap]; v3 = vp_[3 * cap]; v4 = vp_[4 * cap];           \
+        if (fin_) base = fadd(base, fmul(fmul((up_) ? 1.f : -1.f, (float)fin_), (C_))); /* :522 */     \
+        nev += (unsigned)fin_;                                                                         \
+    } while (0)
+                const bool shot_data = SHOT && (meta & kSpShotData);
+                const float shot_I = shot_data ? __uint_as_float(ep[FX_SI * cap]) : 0.f;
+                const float shot_u = shot_data ? __uint_as_float(ep[FX_SU * cap]) : 0.f;
                 if (t < th) {
                     // ---- hot entries: an event in most frames, the chain every round waits for;
                     // straight-line code for every lane, predicated updates
@@ -643,9 +739,18 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                         const unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)(int)cntf);
                         if (wmax > s_max[n] && lane == 0) atomicMax(&s_max[n], wmax);
                         const float C = up ? pos : neg;
-                        const SpEv1 r = sp_classify(ev, gate, cntf, bit, tm, Tr);
-                        if (__any_sync(0xffffffffu, r.slow)) {
-                            if (r.slow) SP_SLOW_FRAME(n, cntf, up, C, bit);
+                        // the marked frame of an entry with shot data: the exact test, inline
+                        bool shot_ev = false, bit_g = bit;
+                        if (bit && shot_data) {
+                            const float thr = fx_shot_thr(up ? s_fr[n].kp : s_fr[n].kn, cfg.shot_inten_m1, shot_I, C);
+                            shot_ev = shot_u * 1024.0f < thr;
+                            bit_g = false;
+                        }
+                        SpEv1 r = sp_classify(ev, gate, cntf, bit_g, tm, Tr);
+                        if (shot_ev) { r.slow = false; r.one = false; }
+                        if (__any_sync(0xffffffffu, r.slow || shot_ev)) {
+                            if (shot_ev) SP_SHOT_FRAME(n, cntf, up, C, shot_I, shot_u);
+                            else if (r.slow) SP_SLOW_FRAME(n, cntf, up, C, bit);
                         }
                         // exactly one event, at ts (:478-502); pol * w is w or -w
                         const float bbf = r.first ? ev.bbf : floorf(r.ts);
@@ -692,6 +797,21 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                         if (!__any_sync(0xffffffffu, n < T)) break;
                         if (n < T) {
                             const bool cross = ad >= den;
+                            if (bit && shot_data) {
+                                // the marked frame of an entry with shot data: the exact test, inline
+                                const float C = up ? pos : neg;
+                                const float thr = fx_shot_thr(up ? s_fr[n].kp : s_fr[n].kn, cfg.shot_inten_m1, shot_I, C);
+                                if (shot_u * 1024.0f < thr) {
+                                    float cq = 0.f;
+                                    if (cross) cq = ad < fadd(den, den) ? 1.f : floorf(fdiv(ad, den));
+                                    if ((unsigned)(int)cq > s_max[n]) atomicMax(&s_max[n], (unsigned)(int)cq);
+                                    SP_SHOT_FRAME(n, cq, up, C, shot_I, shot_u);
+                                    ++n;
+                                    continue;
+                                }
+                                bit = false;
+                                if (!cross) { ++n; continue; }   // not a candidate after all, and no crossing
+                            }
                             // event_counts (:404): 1 below twice the denominator (exact), else the quotient
                             const bool big = cross && !(ad < fadd(den, den));
                             float cntf = cross ? 1.f : 0.f;
@@ -715,6 +835,10 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                             SpEv1 r;
                             r.one = simple; r.slow = false; r.first = true; r.ts = ev.ts1;
                             if (!simple) r = sp_classify(ev, gate, cntf, bit, tm, Tr);
+#ifdef SP_EXP_STAMPS
+                            if (tl && pass == kSpPre)
+                                atomicAdd((unsigned long long*)&tl[24], r.slow ? (bit ? 1ull : (1ull << 16)) : (simple ? (1ull << 48) : (1ull << 32)));
+#endif
                             if (r.slow) {
                                 SP_SLOW_FRAME(n, cntf, up, C, bit);
                             } else if (r.one) {
@@ -737,7 +861,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                     }
                 }
 #ifdef SP_EXP_STAMPS
-                if (tl && pass == 1 && lane == 0) {
+                if (tl && pass == kSpPre && lane == 0) {
                     const long long now = fx_now();
                     if (t == 0) tl[17] = now;
                     if (t == th) tl[19] = now;
@@ -752,34 +876,84 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                     ep[(FX_V0 + 2) * cap] = __float_as_uint(v2);
                     ep[(FX_V0 + 3) * cap] = __float_as_uint(v3);
                     ep[(FX_V0 + 4) * cap] = __float_as_uint(v4);
-                    round_nev += nev;
+                }
+                // statistics of the task's voxel columns (exact integers, order-free): summed over
+                // the warp and added to the tile's partials here, so that no accumulator lives
+                // across the task loop and no separate sweep follows the last task
+                {
+                    FxAcc a;
+                    a.nnz = 0; a.nev = nev; a.s1 = 0; a.lo = 0; a.hi = 0;
+                    fx_stat(v0, a.nnz, a.s1, a.lo, a.hi);
+                    fx_stat(v1, a.nnz, a.s1, a.lo, a.hi);
+                    fx_stat(v2, a.nnz, a.s1, a.lo, a.hi);
+                    fx_stat(v3, a.nnz, a.s1, a.lo, a.hi);
+                    fx_stat(v4, a.nnz, a.s1, a.lo, a.hi);
+                    fx_flush(a, s_acc);
                 }
             }
 #ifdef SP_EXP_STAMPS
-            if (tl && pass == 1 && lane == 0) atomicMax((unsigned long long*)&tl[15], (unsigned long long)fx_now());
+            if (tl && pass == kSpPre && lane == 0) atomicMax((unsigned long long*)&tl[15], (unsigned long long)fx_now());
 #endif
-            // statistics of the voxel columns: a sweep of their own over the table (exact integers,
-            // order-free), so that the task loops above do not carry the accumulators
-            __syncthreads();
-            FxAcc a;
-            a.nnz = 0; a.nev = round_nev; a.s1 = 0; a.lo = 0; a.hi = 0;
-            for (int i = tid; i < n_ent; i += kFxThreads) {
-#pragma unroll
-                for (int b = 0; b < nb; ++b)
-                    fx_stat(__uint_as_float(s_ent[(FX_V0 + b) * cap + i]), a.nnz, a.s1, a.lo, a.hi);
+            if (tid >= 64 && tid < 64 + 2 * kSpNF) {
+                // the single-event entries: per frame cp ON and cn OFF events, all at the frame's
+                // first stamp, i.e. values +-wl in bin bb and +-wr in bin bb+1 (if there is one);
+                // the same exact integers a sweep would add for each of them.  One thread per
+                // (frame, side).
+                const int n = 1 + (tid - 64) % kSpNF, side = (tid - 64) / kSpNF;
+                const long long cp = s_sc[n], cn = s_sc[16 + n];
+                const unsigned long long c = (unsigned long long)(cp + cn);
+                const SpFrameEv ev = s_ev[n];
+                const float w = side ? ev.wr : ev.wl;
+                if (c && side == 0) atomicAdd(&s_acc[4], c);   // events
+                if (c && w != 0.f && !(side && !(ev.bbf + 1.f < (float)nb))) {
+                    const int ip = __float2int_rz(w);
+                    const int fp = __float2int_rz((w - (float)ip) * 2147483648.0f);
+                    const unsigned long long k = ((unsigned long long)ip << 31) + (unsigned long long)fp;   // fx_stat's k, w > 0
+                    const unsigned long long a2lo = k * k, a2hi = __umul64hi(k, k);
+                    const unsigned long long lo = a2lo * c;
+                    const unsigned long long hi = a2hi * c + __umul64hi(a2lo, c);
+                    atomicAdd(&s_acc[0], c);
+                    atomicAdd(&s_acc[1], (unsigned long long)((long long)k * (cp - cn)));
+                    const unsigned long long old = atomicAdd(&s_acc[2], lo);
+                    atomicAdd(&s_acc[3], hi + (old + lo < old ? 1ull : 0ull));
+                }
             }
-            fx_flush(a, s_acc);
-#ifdef SP_EXP_STAMPS
-            if (tl && pass == 1 && lane == 0) atomicMax((unsigned long long*)&tl[22], (unsigned long long)fx_now());
-#endif
         }
         if (n_spill && !pre)
             fx_resolve_spill<FDT, R, false, true>(prm, sq, sm, spill_list, n_spill, tile_px0, spill_vox,
                                                   spill_state, LEAK, SHOT, NOISE == 1, CUTOFF);
         __syncthreads();
         if (pass < 4) FX_STAMP(3 + 3 * pass);
+        if (pre) {
+            // ---- pre-pass barrier: one self-validating word per tile (FxWork::hint) ----------------
+            unsigned long long* slots = fx.hint[pass];
+            if (tid == 0) {
+                unsigned long long w = (unsigned long long)(pass + 1) << 54;
+#pragma unroll
+                for (int n = 1; n < T; ++n) w |= (unsigned long long)min(s_max[n], 63u) << (6 * (n - 1));
+                atomicOr(slots + tile, w);   // (an atomic reaches the L2 at once; a plain store lingers)
+            }
+            if (warp == 0) {
+                // one warp polls (a poller per tile in every CTA floods the L2 with requests)
+                unsigned m[kSpNF];
+#pragma unroll
+                for (int k = 0; k < kSpNF; ++k) m[k] = 0u;
+                for (int i = lane; i < prm.tiles_per_seq; i += 32) {
+                    unsigned long long w;
+                    int spins = 0;
+                    while (((w = fx_ld_relaxed64(slots + i)) >> 54) != (unsigned long long)(pass + 1))
+                        if (++spins > kFxSpin) { s_cnt[2] = 1; w = 0ull; break; }
+#pragma unroll
+                    for (int k = 0; k < kSpNF; ++k) m[k] = max(m[k], (unsigned)(w >> (6 * k)) & 63u);
+                }
+#pragma unroll
+                for (int k = 0; k < kSpNF; ++k) {
+                    const unsigned r = __reduce_max_sync(0xffffffffu, m[k]);
+                    if (lane == 0) s_gmax[k + 1] = r;
+                }
+            }
+        } else {
         // ---- grid barrier of this sequence: accumulate (maxima, partials), arrive, wait, read ------
-        {
             unsigned* gm = fx.gmax[pass];
             unsigned long long* gs = fx.stat[pass];
 #ifdef SP_EXP_NOATOM
@@ -805,7 +979,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 fx_red_release_add(&fx.arrive, 1u);
 #endif
                 if (tl && pass < 3) tl[5 + 3 * pass] = fx_now();
-                const unsigned target = (unsigned)prm.tiles_per_seq * ((unsigned)pass + 1u);
+                const unsigned target = (unsigned)prm.tiles_per_seq * (unsigned)(pass - kSpPre + 1);
                 int spins = 0;
                 while (fx_ld_acquire(&fx.arrive) < target)
                     if (++spins > kFxSpin) { s_cnt[2] = 1; break; }
@@ -835,7 +1009,10 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             const int mx = (pre && s_gmax[tid] == 0) ? s_g[tid].mx : (int)s_gmax[tid];
             set_globals(tid, mx);
         }
-        if (tid < V2E_MAX_FRAMES) { s_max[tid] = 0; s_gmax[tid] = 0; }
+        if (tid < V2E_MAX_FRAMES) {
+            s_max[tid] = (tid >= 1 && tid < T && (s_sc[tid] + s_sc[16 + tid]) > 0) ? 1u : 0u;
+            s_gmax[tid] = 0;
+        }
         if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
         if (tid == 0) s_cnt[5] = 0;
         __syncthreads();
@@ -876,12 +1053,36 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
         const bool norm = s_stat[2] != 0.f;
         for (int i = tid; i < n_ent; i += kFxThreads) {
             const unsigned* ep = s_ent + i;
+            const unsigned meta = ep[FX_META * cap];
             const int p = tile_px0 + (int)ep[FX_IDX * cap];
             sq.base[p] = __uint_as_float(ep[FX_OB * cap]);
-            sq.tmem[p] = __uint_as_float(ep[FX_OT * cap]);
+            float vv[nb];
+            if (meta & kSpStatic) {
+                // static entries: the one event (if any) sits at its frame's first stamp
+                float tm = (meta & 32u) ? 0.f : -Tr;
+                const int f = (int)(meta & 31u);
+#pragma unroll
+                for (int b = 0; b < nb; ++b) vv[b] = 0.f;
+                if (f < T) {
+                    const SpFrameEv ev = s_ev[f];
+                    if (s_g[f].gate) tm = ev.ts1;
+                    const bool up = (meta & kSpStaticUp) != 0u;
+                    const float wl = up ? ev.wl : -ev.wl, wr = up ? ev.wr : -ev.wr;
+#pragma unroll
+                    for (int b = 0; b < nb; ++b) {
+                        if (ev.bbf == (float)b) vv[b] = fadd(0.f, wl);
+                        if (ev.bbf + 1.f == (float)b) vv[b] = fadd(0.f, wr);
+                    }
+                }
+                sq.tmem[p] = tm;
+            } else {
+                sq.tmem[p] = __uint_as_float(ep[FX_OT * cap]);
+#pragma unroll
+                for (int b = 0; b < nb; ++b) vv[b] = __uint_as_float(ep[(FX_V0 + b) * cap]);
+            }
 #pragma unroll
             for (int b = 0; b < nb; ++b) {
-                float v = __uint_as_float(ep[(FX_V0 + b) * cap]);
+                float v = vv[b];
                 if (v != 0.f || !norm) {
                     if (norm) v = fdiv(fsub(v, mean), den);   // nz * (v - mean) / (std + 1e-8)
                     fx_store_vox(cfg, sq.voxel, (size_t)b * P + p, v);
@@ -915,6 +1116,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
         const int used = min(pass + 1, kFxMaxRounds);
         for (int i = tid; i < used * V2E_MAX_FRAMES; i += kFxThreads) (&fx.gmax[0][0])[i] = 0u;
         for (int i = tid; i < used * 8; i += kFxThreads) (&fx.stat[0][0])[i] = 0ull;
+        for (int i = tid; i < kSpPre * kRaMaxTiles; i += kFxThreads) (&fx.hint[0][0])[i] = 0ull;
         __syncthreads();
         if (tid == 0) {
             __threadfence();
