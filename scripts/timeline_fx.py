@@ -26,9 +26,9 @@ for k, fr, tfr in gc.video(1, 5, T, H, W):
           f"spill mean {tl[:,29].mean():.1f} max {tl[:,29].max()} hot mean {tl[:,26].mean():.0f}")
     # NOTE: %globaltimer ticks are ~1.31 ns on this pool (calibrated against CUDA events in
     # scripts/clip_probe.py): multiply the figures below by 1.31 for microseconds
-    rows = [("start", 0), ("setup done", 1), ("pass1 done", 2)]
+    rows = [("start", 0), ("setup done", 1), ("stream done", 8), ("  entries walked", 14), ("  offsets done", 15), ("post pass done", 2)]
     for ps in range(min(npass, 4)):
-        rows += [(f"resolve{ps} done", 3 + 3 * ps)] + ([(f"arrived{ps}", 5 + 3 * ps)] if ps < 3 else []) + [(f"barrier{ps} done", 4 + 3 * ps)]
+        rows += [(f"resolve{ps} done", 3 + 3 * ps)] + ([(f"arrived{ps}", 5 + 3 * ps)] if ps == 2 else []) + [(f"barrier{ps} done", 4 + 3 * ps)]
     rows += [("loop exit", 27), ("commit done", 31)]
     if os.environ.get("V2E_STAMPS"):
         c = tl[:, 24]

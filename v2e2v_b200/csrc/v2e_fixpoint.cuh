@@ -302,7 +302,7 @@ static __device__ __noinline__ void fx_resolve_spill(const FxParams& prm, const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     FxAcc acc;
     acc.nnz = 0; acc.nev = 0; acc.s1 = 0; acc.lo = 0; acc.hi = 0;
-    for (int e0 = warp * 32; e0 < n_spill; e0 += kFxThreads) {
+    for (int e0 = warp * 32; e0 < n_spill; e0 += (int)blockDim.x) {
         const int e = e0 + lane;
         const bool on = e < n_spill;
         const int p = tile_px0 + (on ? (int)spill_list[e] : 0);

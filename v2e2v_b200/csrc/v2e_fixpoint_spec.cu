@@ -24,6 +24,13 @@
 namespace v2e {
 
 constexpr int kSpNF = kFxSpecT - 1;   // frames 1..9 of the pack carry events
+// Threads per CTA.  A 1280x720 tile (6 227 pixels) is 97.3 warp chunks of 64 pixels: 20 warps take
+// them in 4.87 rounds, 24 warps in 4.05 - a fifth round for one chunk; 20 warps also leave each
+// thread 96 registers (no spills in the stream loop).
+#ifndef V2E_SP_THREADS
+#define V2E_SP_THREADS 640
+#endif
+constexpr int kSpThreads = V2E_SP_THREADS;
 #ifndef V2E_SP_HOT_LANES
 #define V2E_SP_HOT_LANES 32
 #endif
@@ -205,7 +212,7 @@ __device__ __forceinline__ SpEv1 sp_classify(const SpFrameEv& ev, bool gate, flo
 }
 
 template <int FDT, int R, int NOISE, bool CUTOFF, bool ONE>
-__global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_constant__ FxParams prm) {
+__global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_constant__ FxParams prm) {
     constexpr bool LEAK = NOISE == 1, SHOT = NOISE == 1;
     constexpr int T = kFxSpecT, nb = kFxSpecNb;
     constexpr int cap = fx_spec_cap(LEAK);
@@ -220,10 +227,10 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     {
         unsigned* d_sq = (unsigned*)(smem_raw + 3840);
         const unsigned* s_sq = (const unsigned*)&blk->sq;
-        for (int i = tid; i < (int)(sizeof(SeqDev) / 4); i += kFxThreads) d_sq[i] = s_sq[i];
+        for (int i = tid; i < (int)(sizeof(SeqDev) / 4); i += kSpThreads) d_sq[i] = s_sq[i];
         unsigned* d_fr = (unsigned*)(smem_raw + 2048);
         const unsigned* s_fr0 = (const unsigned*)&blk->fr[0];
-        for (int i = tid; i < (int)(sizeof(FrameSc) * T / 4); i += kFxThreads) d_fr[i] = s_fr0[i];
+        for (int i = tid; i < (int)(sizeof(FrameSc) * T / 4); i += kSpThreads) d_fr[i] = s_fr0[i];
     }
     __syncthreads();
     const SeqDev& sq = *(const SeqDev*)(smem_raw + 3840);
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
 
     FX_STAMP(1);
     // ================================ pass 1: stream ===============================================
-    for (int c0 = warp * 64; c0 < tile_n; c0 += kFxThreads * 2) {
+    for (int c0 = warp * 64; c0 < tile_n; c0 += kSpThreads * 2) {
         const bool valid = c0 + 2 * lane < tile_n;
         const int l = min(c0 + 2 * lane, tile_n - 2);   // lanes past the end shadow the last pair
         const int p = tile_px0 + l;
@@ -375,18 +382,22 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             }
             if (slot >= 0) {
                 unsigned cm = 0;
+                unsigned* e = s_ent + slot;
                 if (SHOT && o.cand) {
                     if (o.allcand) {
                         cm = 0x1ffu;
                     } else {
+                        float xm = 0.f;   // frame value of the first marked frame
 #pragma unroll
-                        for (int k = 0; k < kSpNF; ++k) {
+                        for (int k = kSpNF - 1; k >= 0; --k) {
                             const unsigned w = k < 3 ? o.w0 : (k < 6 ? o.w1 : o.w2);
-                            if (((w >> (10 * (k % 3))) & 1023u) == 0u) cm |= 1u << k;
+                            if (((w >> (10 * (k % 3))) & 1023u) == 0u) { cm |= 1u << k; xm = x[k]; }
                         }
+                        // inten01 of that frame, for the post pass (an entry with one mark left)
+                        bool bad2 = false;
+                        e[FX_SI * cap] = __float_as_uint(s_lut[sp_index<FDT>(xm, bad2)].y);
                     }
                 }
-                unsigned* e = s_ent + slot;
                 // first active frame 0: found by the post pass
                 e[FX_META * cap] = (o.tm == 0.f ? 32u : 0u) | (cm << 6) | (o.allcand ? 0x20000u : 0u);
                 e[FX_IDX * cap] = (unsigned)(l + j);
@@ -405,11 +416,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             spilled[j] = spill;
             quiet[j] = valid && !spill && slot < 0;
         }
-#ifdef SP_EXP_NOSTORE
-        if (valid && prm.timeline == (long long*)1) {
-#else
         if (valid) {
-#endif
             // no event ever touches the low-pass state: final for every pixel that is not spilled
             // (the spill path recomputes a pixel from its stored state)
             if (CUTOFF) {
@@ -428,9 +435,6 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 if (quiet[1]) { sq.base[p + 1] = base_out[1]; sq.tmem[p + 1] = tm_out[1]; }
             }
             // zero voxel columns; the commit overwrites those of the active pixels
-#ifdef SP_EXP_NOVOX
-            if (prm.timeline == (long long*)1)
-#endif
 #pragma unroll
             for (int b = 0; b < nb; ++b) {
                 if (cfg.voxel_bf16) *(unsigned*)((__nv_bfloat16*)sq.voxel + (size_t)b * P + p) = 0u;
@@ -439,6 +443,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
         }
     }
     __syncthreads();
+    FX_STAMP(8);
     const int n_ent = s_cnt[3];
     const int n_spill = s_cnt[1];
     // ================================ post pass over the table =====================================
@@ -456,11 +461,12 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     // guess, and it is the same for all of them: static entries never enter a resolve round;
     // they are counted per frame and polarity, their statistics follow from the counts, and the
     // commit writes their columns from the final frame constants.
-    for (int i = tid; i < n_ent; i += kFxThreads) {
+    for (int i = tid; i < n_ent; i += kSpThreads) {
         unsigned* ep = s_ent + i;
         unsigned meta = ep[FX_META * cap];
         unsigned cm = (meta >> 6) & 0x3ffu;
         const float pos = __uint_as_float(ep[FX_POS * cap]), neg = __uint_as_float(ep[FX_NEG * cap]);
+        const unsigned cm0 = cm;
         if (SHOT && cm != 0u && !(meta & 0x20000u)) {
             // second stage of the shot test against the same upper bound: a marked frame has
             // field 0, so its uniform is u2 / 1024 with u2 the draw the exact test will use
@@ -475,14 +481,12 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 if (!(fx_shot_uniform<R>(sq.philox_ctr, k + 1, p, 0u) * 1024.0f < tmax)) cm &= ~(1u << k);
             }
             meta = (meta & ~(0x3ffu << 6)) | (cm << 6);
-            if (__popc(cm) == 1) {
-                // the usual survivor: one marked frame.  What its exact test needs besides the
-                // pixel's state - the frame's inten01 and uniform - is fetched once, here, instead
-                // of by an out-of-line call in every resolve round (emulator_utils.py:173-188)
+            if (cm != 0u && cm == (cm0 & (0u - cm0))) {   // one mark left, and it is the first one
+                // the usual survivor: one marked frame, the entry's first mark - the one whose
+                // inten01 pass 1 left in FX_SI.  With the frame's uniform next to it, the exact test
+                // (emulator_utils.py:173-188) runs inline in the resolve rounds instead of through an
+                // out-of-line call each time.
                 const int k1 = __ffs((int)cm) - 1;
-                float L1, I1;
-                log_inten(s_lut, load_frame1<FDT>(sq.frames, (long long)(k1 + 1) * P + p), L1, I1);
-                ep[FX_SI * cap] = __float_as_uint(I1);
                 ep[FX_SU * cap] = __float_as_uint(fx_shot_uniform<R>(sq.philox_ctr, k1 + 1, p, 0u));
                 meta |= kSpShotData;
             }
@@ -543,6 +547,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
         }
     }
     __syncthreads();
+    FX_STAMP(14);
     // ---- order the listed entries by first active frame (counting sort; order within a frame is free)
     if (tid == 0) {
         int o = 0;
@@ -556,8 +561,9 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     }
     if (tid >= 1 && tid < T) s_max[tid] = (s_sc[tid] + s_sc[16 + tid]) > 0 ? 1u : 0u;
     __syncthreads();
+    FX_STAMP(15);
     const int n_cold = s_cnt[4], n_hot = s_cnt[6] - n_cold;
-    for (int i = tid; i < n_ent; i += kFxThreads) {
+    for (int i = tid; i < n_ent; i += kSpThreads) {
         const unsigned meta = s_ent[FX_META * cap + i];
         if (meta & kSpStatic) continue;
         s_perm[atomicAdd(&s_hist[64 + ((meta & 0x10000u) ? 32 : 0) + (int)(meta & 31u)], 1)] = (unsigned short)i;
@@ -580,7 +586,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             // its dependent chain of frames: one hot entry per lane, straight-line code, no voxel
             // accumulation, shot candidates ignored, every event frame taken as the usual single
             // event (gate on) or the plain count (gate off).
-            for (int i0 = warp * 32; i0 < n_hot; i0 += kFxThreads) {
+            for (int i0 = warp * 32; i0 < n_hot; i0 += kSpThreads) {
                 const int i = i0 + lane;
                 const bool on = i < n_hot;
                 const unsigned* ep = s_ent + s_perm[n_cold + (on ? i : 0)];
@@ -956,10 +962,6 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
         // ---- grid barrier of this sequence: accumulate (maxima, partials), arrive, wait, read ------
             unsigned* gm = fx.gmax[pass];
             unsigned long long* gs = fx.stat[pass];
-#ifdef SP_EXP_NOATOM
-            if (prm.timeline != (long long*)1) {
-            } else
-#endif
             if (tid >= 1 && tid < T) {
                 if (s_max[tid]) atomicMax(gm + tid, s_max[tid]);
             } else if (tid >= 32 && tid < 38) {
@@ -973,11 +975,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
             }
             __syncthreads();
             if (tid == 0) {
-#ifdef SP_EXP_RELAXED
-                atomicAdd(&fx.arrive, 1u);
-#else
                 fx_red_release_add(&fx.arrive, 1u);
-#endif
                 if (tl && pass < 3) tl[5 + 3 * pass] = fx_now();
                 const unsigned target = (unsigned)prm.tiles_per_seq * (unsigned)(pass - kSpPre + 1);
                 int spins = 0;
@@ -1051,7 +1049,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     {
         const float mean = s_stat[0], den = s_stat[1];
         const bool norm = s_stat[2] != 0.f;
-        for (int i = tid; i < n_ent; i += kFxThreads) {
+        for (int i = tid; i < n_ent; i += kSpThreads) {
             const unsigned* ep = s_ent + i;
             const unsigned meta = ep[FX_META * cap];
             const int p = tile_px0 + (int)ep[FX_IDX * cap];
@@ -1089,7 +1087,7 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
                 }
             }
         }
-        for (int e = tid; e < n_spill; e += kFxThreads) {
+        for (int e = tid; e < n_spill; e += kSpThreads) {
             const int p = tile_px0 + (int)spill_list[e];
             sq.base[p] = spill_state[p];
             if (CUTOFF) sq.lp[p] = spill_state[(size_t)P + p];
@@ -1114,9 +1112,9 @@ __global__ void __launch_bounds__(kFxThreads, 1) k_fixpoint_spec(const __grid_co
     __syncthreads();
     if (s_cnt[0]) {
         const int used = min(pass + 1, kFxMaxRounds);
-        for (int i = tid; i < used * V2E_MAX_FRAMES; i += kFxThreads) (&fx.gmax[0][0])[i] = 0u;
-        for (int i = tid; i < used * 8; i += kFxThreads) (&fx.stat[0][0])[i] = 0ull;
-        for (int i = tid; i < kSpPre * kRaMaxTiles; i += kFxThreads) (&fx.hint[0][0])[i] = 0ull;
+        for (int i = tid; i < used * V2E_MAX_FRAMES; i += kSpThreads) (&fx.gmax[0][0])[i] = 0u;
+        for (int i = tid; i < used * 8; i += kSpThreads) (&fx.stat[0][0])[i] = 0ull;
+        for (int i = tid; i < kSpPre * kRaMaxTiles; i += kSpThreads) (&fx.hint[0][0])[i] = 0ull;
         __syncthreads();
         if (tid == 0) {
             __threadfence();
@@ -1143,7 +1141,7 @@ static int launch_spec_1(const FxParams& prm, int grid, size_t smem, int optin, 
         attr_set = true;
     }
     void* args[] = {(void*)&prm};
-    rc = cuda_ok(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(kFxThreads),
+    rc = cuda_ok(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3(kSpThreads),
                                              args, smem, st));
     count_launch();
     return rc;
