@@ -201,14 +201,18 @@ static __device__ __noinline__ float shot_uniform(unsigned long long ctr64, int 
 // Geometric skip: index of the first success of iid Bernoulli(p) trials, from one uniform:
 // floor(log1p(-u)/log1p(-p)).  Both arguments are tiny in practice (u < bound ~ 5e-4), where the
 // series -log1p(-x) = x + x^2/2 + x^3/3 + x^4/4 (relative error < x^4) is exact to f32 rounding.
+// the small-argument branch on its own (u < 0.03, 0 < p < 0.03), for callers that stay inline
+__device__ __forceinline__ float geometric_skip_small(float u, float p) {
+    const float lu = u * fmaf(u, fmaf(u, fmaf(u, 0.25f, 0.33333334f), 0.5f), 1.0f);
+    const float lq = p * fmaf(p, fmaf(p, fmaf(p, 0.25f, 0.33333334f), 0.5f), 1.0f);
+    return floorf(__fdividef(lu, lq));
+}
 static __device__ __noinline__ int geometric_skip(float u, float p) {
     if (!(p > 0.f)) return 0x7fffffff;
     if (p >= 1.f) return 0;
     float g;
     if (u < 0.03f && p < 0.03f) {
-        const float lu = u * fmaf(u, fmaf(u, fmaf(u, 0.25f, 0.33333334f), 0.5f), 1.0f);
-        const float lq = p * fmaf(p, fmaf(p, fmaf(p, 0.25f, 0.33333334f), 0.5f), 1.0f);
-        g = floorf(__fdividef(lu, lq));
+        g = geometric_skip_small(u, p);
     } else {
         g = (float)floor(log1p(-(double)u) / log1p(-(double)p));
     }

@@ -35,6 +35,10 @@ constexpr int kSpThreads = V2E_SP_THREADS;
 #define V2E_SP_HOT_LANES 32
 #endif
 constexpr int kSpHotLanes = V2E_SP_HOT_LANES;   // entries per task of the hot list
+#ifndef V2E_SP_COLD_LANES
+#define V2E_SP_COLD_LANES 32
+#endif
+constexpr int kSpColdLanes = V2E_SP_COLD_LANES;   // entries per task of the cold list
 #ifndef V2E_SP_PRE
 #define V2E_SP_PRE 2
 #endif
@@ -211,6 +215,73 @@ __device__ __forceinline__ SpEv1 sp_classify(const SpFrameEv& ev, bool gate, flo
     return r;
 }
 
+// What the exact shot test of a marked frame needs when the entry does not carry it (several marks
+// survived the post pass, or not the first one): the frame's inten01 and uniform, fetched on the
+// spot.  A marked frame has field 0 (entries whose every frame is a candidate are not served
+// here), so the uniform is fx_shot_uniform(.., field 0).  False: not an integer-valued frame.
+template <int FDT, int R>
+__device__ __forceinline__ bool sp_mark_data(const SeqDev& sq, const float2* s_lut, int P, int n, int p,
+                                             float& I, float& u) {
+    const float x = load_frame1<FDT>(sq.frames, (long long)n * P + p);
+    const int v = __float2int_rn(x);
+    if (!((float)v == x && (unsigned)v < 256u)) return false;
+    I = s_lut[v].y;
+    const uint4 w = noise_words<R>(sq.philox_ctr, (unsigned)n, (unsigned)p, 1);
+    u = (0.f + (float)w.x * (1.0f / 4294967296.0f)) * (1.0f / 1024.0f);
+    return true;
+}
+
+// A frame whose shot candidate is real (the exact first-stage test passed), without the generic
+// iteration loop (iterate_pixel, shot_mode 2) in the usual cases:
+//   kind 0 - the frame is as if unmarked: the first firing falls beyond the frame's iterations, or
+//            on an iteration that carries an event of the pixel's own anyway;
+//   kind 1 - after the pixel's own events (iterations [0, cnt), possibly none) the shot fires once,
+//            at stamp ts of a later iteration (the refractory gate is the caller's);
+//   kind 2 - anything else (a second firing within the frame, arguments outside the small-argument
+//            branch of geometric_skip): the generic code.  r.ts then says why (development builds).
+// sa: this frame's (rate/2)*dt / num_iters (emulator_utils.py:174), in the precision the reference
+// uses for it (trap T5).  Same arithmetic and draws as iterate_pixel, hence the same results.
+struct SpShot {
+    int kind;
+    float ts;
+};
+template <int R>
+__device__ __forceinline__ SpShot sp_shot_lean(const CfgDev& cfg, const SeqDev& sq, double sa, bool f64,
+                                               const SpFrameEv& ev, int n, int p, bool up, float C,
+                                               float cntf, float I, float u) {
+    SpShot r;
+    r.kind = 2;
+    r.ts = 0.f;
+    if (!(ev.mxf >= 1.f) || !(ev.mxf <= 24.f)) return r;
+    const float fac = fadd(fmul(cfg.shot_inten_m1, I), 1.0f);
+    const float pp = fmul(up ? cfg.rn_pos : cfg.rn_neg, C);
+    float p_it;
+    if (f64) p_it = (float)__dmul_rn(__dmul_rn(sa, (double)fac), (double)pp);
+    else p_it = fmul(fmul((float)sa, fac), pp);
+    if (!(p_it > 0.f && p_it < 1e-3f && u < 0.03f)) return r;
+    const float g = geometric_skip_small(u, p_it);   // iteration of the first firing
+    if (!(g < ev.mxf)) {
+        r.kind = 0;
+        return r;
+    }
+    // the next firing, from a fresh uniform (drawn when the loop reaches the first one).  It lies
+    // beyond the frame whenever the uniform is not tiny: log1p(-0.03) / log1p(-p) > 30 iterations
+    // for p < 1e-3 and a frame has at most 24 here, so those logarithms are never formed.
+    const uint4 w = noise_words<R>(sq.philox_ctr, (unsigned)n, (unsigned)p, 2u);
+    const float u2 = (float)(w.x >> 8) * (1.0f / 16777216.0f);
+    if (!(u2 >= 0.03f)) {
+        r.ts = 2.f;
+        if (!(g + 1.f + geometric_skip_small(u2, p_it) >= ev.mxf)) return r;
+    }
+    if (g < cntf) {
+        r.kind = 0;
+        return r;
+    }
+    r.kind = 1;
+    r.ts = fadd(ev.t0, fmul(ev.step, g + 1.f));   // stamp of iteration g (:419)
+    return r;
+}
+
 template <int FDT, int R, int NOISE, bool CUTOFF, bool ONE>
 __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_constant__ FxParams prm) {
     constexpr bool LEAK = NOISE == 1, SHOT = NOISE == 1;
@@ -250,6 +321,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     int* s_cnt = (int*)(smem_raw + 3792);   // [0] slot counter, [1] spilled, [2] error, [3] entries, [5] task counter
     float* s_stat = (float*)(smem_raw + 3824);                           // mean, den, on, theta
     int* s_sc = (int*)(smem_raw + 2944);    // 2 x 16: single-event entries per frame, ON / OFF
+    double* s_sa = (double*)(smem_raw + 3200);   // 10 doubles in the unused tail of s_g (frames >= T)
     unsigned short* s_perm = (unsigned short*)(smem_raw + kFxPermOff);
     int* s_hist = (int*)(smem_raw + kFxPermOff + 2 * kFxPermMax);        // 2 x 64 ints
     unsigned* s_ent = (unsigned*)(smem_raw + kFxHeader);
@@ -286,6 +358,9 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         e.wl = fsub(1.0f, d);
         e.wr = d;
         s_ev[n] = e;
+        if (SHOT && mx > 0)   // iterate_pixel's a64 / a32 (emulator_utils.py:174, trap T5)
+            s_sa[n] = ((sq.shot_f64_mask >> n) & 1u) ? s_fr[n].shot_c / (double)mx
+                                                    : (double)fdiv((float)s_fr[n].shot_c, (float)mx);
     };
     if (tid < V2E_MAX_FRAMES) {
         // the guess: last pack's maxima (a hint kept in the workspace; any value is correct)
@@ -295,7 +370,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         s_gmax[tid] = 0;
     }
     if (tid < 5) { s_acc[tid] = 0ull; s_tot[tid] = 0ull; }
-    if (tid < 8) s_cnt[tid] = 0;
+    if (tid < 8) s_cnt[tid] = tid == 3 ? 0x7fffffff : 0;
     if (tid < 128) s_hist[tid] = 0;
     if (tid < 32) s_sc[tid] = 0;
     __syncthreads();
@@ -317,6 +392,14 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
 
     FX_STAMP(1);
     // ================================ pass 1: stream ===============================================
+    // row and column of the warp's chunk, carried along instead of divided out per pixel
+    int ch_y, ch_x;
+    {
+        const int q = tile_px0 + warp * 64;
+        ch_y = q / cfg.W;
+        ch_x = q - ch_y * cfg.W;
+    }
+    const int ch_dy = (kSpThreads * 2) / cfg.W, ch_dx = (kSpThreads * 2) - ch_dy * cfg.W;
     for (int c0 = warp * 64; c0 < tile_n; c0 += kSpThreads * 2) {
         const bool valid = c0 + 2 * lane < tile_n;
         const int l = min(c0 + 2 * lane, tile_n - 2);   // lanes past the end shadow the last pair
@@ -337,8 +420,12 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         for (int k = 0; k < kSpNF; ++k) x2[k] = sp_load_frame2<FDT>(sq.frames, (long long)(k + 1) * P + p);
         // sensing-diversity pattern: even row AND even column (v2e_model.py:194,211); W is even,
         // so only the pair's first pixel can sit on an even column
-        const int yrow = p / cfg.W;
-        const bool small0 = ((yrow | (p - yrow * cfg.W)) & 1) == 0;
+        int yrow = ch_y, xcol = ch_x + (l - c0);
+        while (xcol >= cfg.W) { xcol -= cfg.W; ++yrow; }
+        const bool small0 = ((yrow | xcol) & 1) == 0;
+        ch_y += ch_dy;
+        ch_x += ch_dx;
+        if (ch_x >= cfg.W) { ch_x -= cfg.W; ++ch_y; }
 
         float lp_out[2], base_out[2], tm_out[2];
         bool quiet[2], spilled[2];
@@ -366,8 +453,10 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
             if (am) {
                 int s0 = 0;
                 if (lane == 0) {
+                    // allocations only grow: the first one that does not fit ends the table where it
+                    // starts, and nothing after it fits either
                     s0 = atomicAdd(&s_cnt[0], __popc(am));
-                    if (s0 + __popc(am) <= cap) atomicMax(&s_cnt[3], s0 + __popc(am));
+                    if (s0 + __popc(am) > cap) atomicMin(&s_cnt[3], s0);
                 }
                 s0 = __shfl_sync(0xffffffffu, s0, 0);
                 if (want && s0 + __popc(am) <= cap) slot = s0 + __popc(am & ((1u << lane) - 1u));
@@ -396,6 +485,9 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                         // inten01 of that frame, for the post pass (an entry with one mark left)
                         bool bad2 = false;
                         e[FX_SI * cap] = __float_as_uint(s_lut[sp_index<FDT>(xm, bad2)].y);
+                        // marked entries are listed (in the space of the entry order, which is built
+                        // later): their marks are refined before the post pass, a few lanes per warp
+                        s_perm[atomicAdd(&s_cnt[7], 1)] = (unsigned short)slot;
                     }
                 }
                 // first active frame 0: found by the post pass
@@ -427,7 +519,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                     if (!spilled[1]) sq.lp[p + 1] = lp_out[1];
                 }
             }
-            if (quiet[0] && quiet[1]) {
+            // (an active pixel's words are written again by the commit; nothing reads them before)
+            if (!spilled[0] && !spilled[1]) {
                 *(float2*)(sq.base + p) = make_float2(base_out[0], base_out[1]);
                 *(float2*)(sq.tmem + p) = make_float2(tm_out[0], tm_out[1]);
             } else {
@@ -444,7 +537,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     }
     __syncthreads();
     FX_STAMP(8);
-    const int n_ent = s_cnt[3];
+    const int n_ent = min(s_cnt[3], s_cnt[0]);
     const int n_spill = s_cnt[1];
     // ================================ post pass over the table =====================================
     // Per entry: first active frame f (exact test, v2e_model.py:394-404), brightness before it,
@@ -461,24 +554,32 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     // guess, and it is the same for all of them: static entries never enter a resolve round;
     // they are counted per frame and polarity, their statistics follow from the counts, and the
     // commit writes their columns from the final frame constants.
-    for (int i = tid; i < n_ent; i += kSpThreads) {
-        unsigned* ep = s_ent + i;
-        unsigned meta = ep[FX_META * cap];
-        unsigned cm = (meta >> 6) & 0x3ffu;
-        const float pos = __uint_as_float(ep[FX_POS * cap]), neg = __uint_as_float(ep[FX_NEG * cap]);
-        const unsigned cm0 = cm;
-        if (SHOT && cm != 0u && !(meta & 0x20000u)) {
-            // second stage of the shot test against the same upper bound: a marked frame has
-            // field 0, so its uniform is u2 / 1024 with u2 the draw the exact test will use
-            // (fx_event_frame); four marks in five go away here, one lane per entry, instead of
-            // costing a resolve task an out-of-line call every round
+    if (SHOT) {
+        // ---- marked entries first: second stage of the shot test against the same upper bound.  A
+        // marked frame has field 0, so its uniform is u2 / 1024 with u2 the draw the exact test will
+        // use (fx_event_frame); four marks in five go away here instead of costing a resolve task an
+        // out-of-line call every round.  The list is short (one pixel in a hundred): it is dealt
+        // across the warps, so that no warp walks more than a few of these divergent chains.
+        const int n_mark = s_cnt[7];
+        constexpr int nwarps = kSpThreads / 32;
+        for (int j = lane * nwarps + warp; j < n_mark; j += 32 * nwarps) {
+            unsigned* ep = s_ent + s_perm[j];
+            unsigned meta = ep[FX_META * cap];
+            const unsigned cm0 = (meta >> 6) & 0x3ffu;
+            unsigned cm = cm0;
+            float u_first = 0.f;   // the uniform of the entry's first mark
             const int p = tile_px0 + (int)ep[FX_IDX * cap];
-            const float cmax = fmaxf(pos, neg);
-            for (int k = 0; k < kSpNF; ++k) {
-                if (!((cm >> k) & 1u)) continue;
+            const float cmax = fmaxf(__uint_as_float(ep[FX_POS * cap]), __uint_as_float(ep[FX_NEG * cap]));
+            for (unsigned m = cm0; m != 0u; m &= m - 1u) {
+                const int k = __ffs((int)m) - 1;
                 const float tmax = (fmaxf(s_fr[k + 1].kp, s_fr[k + 1].kn) * 4.0f *
                                     (1.0f + fmaxf(cfg.shot_inten_m1, 0.f))) * cmax;
-                if (!(fx_shot_uniform<R>(sq.philox_ctr, k + 1, p, 0u) * 1024.0f < tmax)) cm &= ~(1u << k);
+                // (fx_shot_uniform, inline: a call here would park the loop's registers in local
+                // memory, an L2 round trip each with the L1 carved out as shared memory)
+                const uint4 w = noise_words<R>(sq.philox_ctr, (unsigned)(k + 1), (unsigned)p, 1);
+                const float u = (0.f + (float)w.x * (1.0f / 4294967296.0f)) * (1.0f / 1024.0f);
+                if (!(u * 1024.0f < tmax)) cm &= ~(1u << k);
+                if (k == __ffs((int)cm0) - 1) u_first = u;
             }
             meta = (meta & ~(0x3ffu << 6)) | (cm << 6);
             if (cm != 0u && cm == (cm0 & (0u - cm0))) {   // one mark left, and it is the first one
@@ -486,61 +587,69 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                 // inten01 pass 1 left in FX_SI.  With the frame's uniform next to it, the exact test
                 // (emulator_utils.py:173-188) runs inline in the resolve rounds instead of through an
                 // out-of-line call each time.
-                const int k1 = __ffs((int)cm) - 1;
-                ep[FX_SU * cap] = __float_as_uint(fx_shot_uniform<R>(sq.philox_ctr, k1 + 1, p, 0u));
+                ep[FX_SU * cap] = __float_as_uint(u_first);
                 meta |= kSpShotData;
             }
+            ep[FX_META * cap] = meta;
         }
-        float base = __uint_as_float(ep[FX_BASE * cap]);
-        const float base0 = base;
-        int f = 0;
-        float sb = 0.f, bs = 0.f;
-        bool hot = false, one = false, more = false, up1 = false;
-        int ncross = 0;
+        __syncthreads();
+        FX_STAMP(23);
+    }
+    for (int i = tid; i < n_ent; i += kSpThreads) {
+        unsigned* ep = s_ent + i;
+        const unsigned meta = ep[FX_META * cap];
+        const unsigned cm = SHOT ? (meta >> 6) & 0x3ffu : 0u;
+        const float pos = __uint_as_float(ep[FX_POS * cap]), neg = __uint_as_float(ep[FX_NEG * cap]);
+        // One chain: up to the first active frame c is the brightness the pixel really has (no event
+        // yet: base less the leak, :366-371); from there on it is the brightness it would have if
+        // every crossing gave exactly one event (:522 with final = 1) - what the static test and the
+        // busy hint need.  Before the first active frame a crossing IS the first active frame, so the
+        // chain steps at every crossing, whatever came before.  What happened where is kept as one
+        // bit per frame and sorted out after the loop.
+        float c = __uint_as_float(ep[FX_BASE * cap]);
+        const float base0 = c;
+        const float denp = fadd(pos, 1e-9f), denn = fadd(neg, 1e-9f), nneg = -neg;
+        const float tp = theta * pos, tn = theta * neg;
+        unsigned xmask = 0u, umask = 0u, amask = 0u;   // crossing / diff > 0 / a polarity (|diff| > 1e-6)
+        float sb = c, adf = 0.f, denf = 1.f;           // at the first active frame (so far: none)
+        bool seen = false, hot = false;
 #pragma unroll
         for (int k = 0; k < kSpNF; ++k) {
             const float nw = __uint_as_float(ep[(nw_off + k) * cap]);
-            const float dlk = LEAK ? __uint_as_float(ep[(dl_off + k) * cap]) : 0.f;
-            const float b = LEAK ? fsub(base, dlk) : base;
+            const float b = LEAK ? fsub(c, __uint_as_float(ep[(dl_off + k) * cap])) : c;
             const float diff = fsub(nw, b);
             const float ad = fabsf(diff);
             const bool up = diff > 0.f;
-            const float den = fadd(up ? pos : neg, 1e-9f);
-            const bool hit = !f && ad > 1e-6f && (ad >= den || ((cm >> k) & 1u));
-            if (f) {
-                // after the first active frame: would anything else happen had it been one event?
-                // (and, as a scheduling hint, how many more frames cross if each gives one event)
-                const float b2 = LEAK ? fsub(bs, dlk) : bs;
-                const float d2 = fsub(nw, b2);
-                const bool x2 = fabsf(d2) >= fadd(d2 > 0.f ? pos : neg, 1e-9f);
-                more = more || x2;
-                ncross += x2 ? 1 : 0;
-                bs = x2 ? (d2 > 0.f ? fadd(b2, pos) : fadd(b2, -neg)) : b2;
-            }
-            if (hit) {
-                f = k + 1;
-                sb = base;
-                one = ad >= den && ad < fadd(den, den) && cm == 0u && !(meta & 32u);
-                up1 = up;
-                bs = up ? fadd(b, pos) : fadd(b, -neg);   // :522 with one event: base + pol * C
-            }
+            const float den = up ? denp : denn;
+            const bool cross = ad >= den;   // den > 1e-6: the tolerance mask (:394) holds
+            if (!seen) { sb = c; adf = ad; denf = den; }
+            if (cross) xmask |= 1u << k;
+            if (up) umask |= 1u << k;
+            if (SHOT && ad > 1e-6f) amask |= 1u << k;
+            // the first active frame: a crossing, or a shot candidate with a polarity (:394-404,:447)
+            seen = seen || cross || (SHOT && ((cm >> k) & 1u) && ad > 1e-6f);
+            c = cross ? fadd(b, up ? pos : nneg) : b;   // :522 with one event: base + pol * C
             const float d0 = fsub(nw, base0);
-            hot = hot || fabsf(d0) >= theta * (d0 > 0.f ? pos : neg);
-            if (!f) base = b;
+            hot = hot || fabsf(d0) >= (d0 > 0.f ? tp : tn);
         }
-        // busy entries (an event in four frames or more) join the hot list: its frame-synchronous
+        const unsigned act = xmask | (cm & amask);
+        const bool idle = act == 0u;
+        int f = idle ? 31 : __ffs((int)act);
+        const unsigned later = idle ? 0u : (xmask >> f);   // crossings after the first active frame
+        const bool up1 = !idle && ((umask >> (f - 1)) & 1u);
+        // exactly one event: the first active frame crosses by one threshold, the pixel has no shot
+        // mark and no event earlier in the pack (:469-472), and nothing crosses afterwards
+        const bool one = !idle && ((xmask >> (f - 1)) & 1u) && adf < fadd(denf, denf) && cm == 0u && !(meta & 32u);
+        // busy entries (an event in three frames or more) join the hot list: its frame-synchronous
         // straight-line loop beats the event-driven one when most frames hold an event
-        hot = hot || ncross >= kSpBusy;
-        const bool idle = !f;
-        if (idle) { f = 31; sb = base; bs = base; }   // nothing happens: the entry only carries its state
-        const bool stat = idle || (one && !more);
+        hot = hot || __popc(later) >= kSpBusy;
+        if (idle) sb = c;   // nothing happens: the entry only carries its state
+        const bool stat = idle || (one && later == 0u);
         ep[FX_META * cap] = meta | (unsigned)f | (hot ? 0x10000u : 0u) | (stat ? kSpStatic : 0u) |
                             (up1 ? kSpStaticUp : 0u);
         ep[FX_BASE * cap] = __float_as_uint(sb);
         if (stat) {
-            ep[FX_OB * cap] = __float_as_uint(bs);
-#pragma unroll
-            for (int b = 0; b < nb; ++b) ep[(FX_V0 + b) * cap] = 0u;   // the statistics sweep reads these
+            ep[FX_OB * cap] = __float_as_uint(c);
             if (!idle) atomicAdd(&s_sc[(up1 ? 0 : 16) + f], 1);
         } else {
             atomicAdd(&s_hist[(hot ? 32 : 0) + f], 1);
@@ -570,7 +679,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     }
     __syncthreads();
     FX_STAMP(2);
-    if (tl && tid == 0) { tl[28] = n_ent; tl[29] = n_spill; tl[26] = n_hot; }
+    if (tl && tid == 0) { tl[28] = n_ent; tl[29] = n_spill; tl[26] = n_hot; tl[25] = n_cold; }
 
     // ================================ resolve rounds ================================================
     // round 0 is a pre-pass over the hot entries only: under last pack's guess it yields the
@@ -649,7 +758,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
             // paths, so fewer lanes per warp shorten the chain every round waits for), then the
             // cold list in tasks of 32; each list in the order of the first active frame, so that
             // a task only walks the frames its entries need
-            const int th = (n_hot + kSpHotLanes - 1) / kSpHotLanes, tc = (n_cold + 31) >> 5;
+            const int th = (n_hot + kSpHotLanes - 1) / kSpHotLanes, tc = (n_cold + kSpColdLanes - 1) / kSpColdLanes;
             while (true) {
                 int t = 0;
                 if (lane == 0) t = atomicAdd(&s_cnt[5], 1);
@@ -662,17 +771,13 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                     on = lane < kSpHotLanes && i < n_hot;
                     e = s_perm[n_cold + (on ? i : 0)];
                 } else {
-                    const int i = (t - th) * 32 + lane;
-                    on = i < n_cold;
+                    const int i = (t - th) * kSpColdLanes + lane;
+                    on = lane < kSpColdLanes && i < n_cold;
                     e = s_perm[on ? i : 0];
                 }
 #ifdef SP_EXP_STAMPS
-                if (tl && pass == kSpPre && lane == 0) {
-                    const long long now = fx_now();
-                    if (t == 0) tl[16] = now;
-                    if (t == th) tl[18] = now;
-                    if (t == th + tc - 1) tl[20] = now;
-                }
+                const long long task_t0 = fx_now();
+                long long slow_t = 0;
 #endif
                 unsigned* ep = s_ent + e;
                 const unsigned meta = ep[FX_META * cap];
@@ -693,8 +798,16 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                 // (out of line), accumulators via the entry's voxel words.  A macro, not a lambda:
                 // a closure that is not inlined would pin base, tm and the accumulators to local
                 // memory for the whole loop.
+#ifdef SP_EXP_STAMPS
+#define SP_T0 const long long t0_ = fx_now();
+#define SP_T1 if (tl && pass == kSpPre) { slow_t += fx_now() - t0_; atomicMax((unsigned long long*)&tl[22], (unsigned long long)(fx_now() - t0_)); atomicAdd((unsigned long long*)&tl[21], (unsigned long long)(fx_now() - t0_)); }
+#else
+#define SP_T0
+#define SP_T1
+#endif
 #define SP_SLOW_FRAME(n_, cntf_, up_, C_, bit_)                                                        \
     do {                                                                                               \
+        SP_T0                                                                                          \
         float* vp_ = (float*)(ep + FX_V0 * cap);                                                       \
         vp_[0] = v0; vp_[cap] = v1; vp_[2 * cap] = v2; vp_[3 * cap] = v3; vp_[4 * cap] = v4;           \
         const unsigned long long r_ = fx_event_frame<FDT, R, false>(                                   \
@@ -705,11 +818,13 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         v0 = vp_[0]; v1 = vp_[cap]; v2 = vp_[2 * cap]; v3 = vp_[3 * cap]; v4 = vp_[4 * cap];           \
         if (fin_) base = fadd(base, fmul(fmul((up_) ? 1.f : -1.f, (float)fin_), (C_))); /* :522 */     \
         nev += (unsigned)fin_;                                                                         \
+        SP_T1                                                                                          \
     } while (0)
                 // a shot candidate whose inten01 and uniform are at hand: straight to the iteration
                 // loop (what fx_event_frame does once it has decided `cand`)
 #define SP_SHOT_FRAME(n_, cntf_, up_, C_, I_, u_)                                                       \
     do {                                                                                               \
+        SP_T0                                                                                          \
         float* vp_ = (float*)(ep + FX_V0 * cap);                                                       \
         vp_[0] = v0; vp_[cap] = v1; vp_[2 * cap] = v2; vp_[3 * cap] = v3; vp_[4 * cap] = v4;           \
         const FrameGlobals g_ = s_g[(n_)];                                                             \
@@ -721,6 +836,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         v0 = vp_[0]; v1 = vp_[cap]; v2 = vp_[2 * cap]; v3 = vp_[3 * cap]; v4 = vp_[4 * cap];           \
         if (fin_) base = fadd(base, fmul(fmul((up_) ? 1.f : -1.f, (float)fin_), (C_))); /* :522 */     \
         nev += (unsigned)fin_;                                                                         \
+        SP_T1                                                                                          \
     } while (0)
                 const bool shot_data = SHOT && (meta & kSpShotData);
                 const float shot_I = shot_data ? __uint_as_float(ep[FX_SI * cap]) : 0.f;
@@ -747,17 +863,44 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                         const float C = up ? pos : neg;
                         // the marked frame of an entry with shot data: the exact test, inline
                         bool shot_ev = false, bit_g = bit;
-                        if (bit && shot_data) {
-                            const float thr = fx_shot_thr(up ? s_fr[n].kp : s_fr[n].kn, cfg.shot_inten_m1, shot_I, C);
-                            shot_ev = shot_u * 1024.0f < thr;
+                        float fI = shot_I, fu = shot_u;
+                        bool have = bit && shot_data;
+                        if (has_cm && __any_sync(0xffffffffu, bit && !shot_data && !(meta & 0x20000u))) {
+                            if (bit && !shot_data && !(meta & 0x20000u))
+                                have = sp_mark_data<FDT, R>(sq, s_lut, P, n, p, fI, fu);
+                        }
+                        if (have) {
+                            const float thr = fx_shot_thr(up ? s_fr[n].kp : s_fr[n].kn, cfg.shot_inten_m1, fI, C);
+                            shot_ev = fu * 1024.0f < thr;
                             bit_g = false;
                         }
                         SpEv1 r = sp_classify(ev, gate, cntf, bit_g, tm, Tr);
-                        if (shot_ev) { r.slow = false; r.one = false; }
+                        float xts = -1.f;   // stamp of a shot event that follows the pixel's own events
                         if (__any_sync(0xffffffffu, r.slow || shot_ev)) {
-                            if (shot_ev) SP_SHOT_FRAME(n, cntf, up, C, shot_I, shot_u);
-                            else if (r.slow) SP_SLOW_FRAME(n, cntf, up, C, bit);
+                            if (shot_ev) {
+                                const SpShot sh = sp_shot_lean<R>(cfg, sq, s_sa[n], (sq.shot_f64_mask >> n) & 1u,
+                                                                  ev, n, p, up, C, cntf, fI, fu);
+                                // (kind 0: r stands - it was formed as for an unmarked frame)
+                                if (sh.kind == 1 && !r.slow) {
+                                    xts = sh.ts;
+                                } else if (sh.kind != 0) {
+                                    r.slow = false;
+                                    r.one = false;
+#ifdef SP_EXP_STAMPS
+                                    if (tl && pass == kSpPre) atomicAdd((unsigned long long*)&tl[20], 1ull << (16 * (sh.kind == 2 ? (int)sh.ts : 1)));
+#endif
+                                    SP_SHOT_FRAME(n, cntf, up, C, fI, fu);
+                                }
+                            }
+                            if (r.slow) {
+                                r.one = false;
+#ifdef SP_EXP_STAMPS
+                                if (tl && pass == kSpPre) atomicAdd((unsigned long long*)&tl[20], 1ull << (bit ? 48 : 56));
+#endif
+                                SP_SLOW_FRAME(n, cntf, up, C, bit);
+                            }
                         }
+                        const float base_pre = base;
                         // exactly one event, at ts (:478-502); pol * w is w or -w
                         const float bbf = r.first ? ev.bbf : floorf(r.ts);
                         float wr = r.first ? ev.wr : fsub(r.ts, bbf);
@@ -776,6 +919,25 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                             if (gate) tm = r.ts;
                             base = fadd(base, up ? C : -C);   // :522: (pol * 1) * C
                             nev += 1u;
+                        }
+                        if (__any_sync(0xffffffffu, xts >= 0.f)) {
+                            // the shot event, after the pixel's own (:449-502 at a later iteration)
+                            if (xts >= 0.f && (!gate || fsub(xts, tm) > Tr)) {
+                                if (gate) tm = xts;
+                                const float xb = floorf(xts);
+                                float xr = fsub(xts, xb);
+                                float xl = fsub(1.0f, xr);
+                                if (!up) { xl = -xl; xr = -xr; }
+                                if (xb == 0.f) { v0 = fadd(v0, xl); v1 = fadd(v1, xr); }
+                                else if (xb == 1.f) { v1 = fadd(v1, xl); v2 = fadd(v2, xr); }
+                                else if (xb == 2.f) { v2 = fadd(v2, xl); v3 = fadd(v3, xr); }
+                                else if (xb == 3.f) { v3 = fadd(v3, xl); v4 = fadd(v4, xr); }
+                                else if (xb == 4.f) { v4 = fadd(v4, xl); }
+                                // :522 with final = 1 or 2: (pol * final) * C, 2C being exact
+                                const float st = r.one ? fadd(C, C) : C;
+                                base = fadd(base_pre, up ? st : -st);
+                                nev += 1u;
+                            }
                         }
                     }
                 } else {
@@ -803,20 +965,35 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                         if (!__any_sync(0xffffffffu, n < T)) break;
                         if (n < T) {
                             const bool cross = ad >= den;
-                            if (bit && shot_data) {
-                                // the marked frame of an entry with shot data: the exact test, inline
+                            float xts = -1.f;   // stamp of a shot event that follows the pixel's own events
+                            float fI = shot_I, fu = shot_u;
+                            bool have = bit && shot_data;
+                            if (bit && !shot_data && !(meta & 0x20000u))
+                                have = sp_mark_data<FDT, R>(sq, s_lut, P, n, p, fI, fu);
+                            if (have) {
+                                // a marked frame: the exact test, inline
                                 const float C = up ? pos : neg;
-                                const float thr = fx_shot_thr(up ? s_fr[n].kp : s_fr[n].kn, cfg.shot_inten_m1, shot_I, C);
-                                if (shot_u * 1024.0f < thr) {
+                                const float thr = fx_shot_thr(up ? s_fr[n].kp : s_fr[n].kn, cfg.shot_inten_m1, fI, C);
+                                if (fu * 1024.0f < thr) {
                                     float cq = 0.f;
                                     if (cross) cq = ad < fadd(den, den) ? 1.f : floorf(fdiv(ad, den));
                                     if ((unsigned)(int)cq > s_max[n]) atomicMax(&s_max[n], (unsigned)(int)cq);
-                                    SP_SHOT_FRAME(n, cq, up, C, shot_I, shot_u);
-                                    ++n;
-                                    continue;
+                                    const SpFrameEv evs = s_ev[n];
+                                    const SpShot sh = sp_shot_lean<R>(cfg, sq, s_sa[n], (sq.shot_f64_mask >> n) & 1u,
+                                                                      evs, n, p, up, C, cq, fI, fu);
+                                    if (sh.kind == 2) {
+#ifdef SP_EXP_STAMPS
+                                        if (tl && pass == kSpPre) atomicAdd((unsigned long long*)&tl[20], (1ull << (16 * (int)sh.ts)) << 8);
+#endif
+                                        SP_SHOT_FRAME(n, cq, up, C, fI, fu);
+                                        ++n;
+                                        continue;
+                                    }
+                                    if (sh.kind == 1) xts = sh.ts;
+                                    // (kind 0: as if unmarked)
                                 }
                                 bit = false;
-                                if (!cross) { ++n; continue; }   // not a candidate after all, and no crossing
+                                if (!cross && xts < 0.f) { ++n; continue; }   // not a candidate after all, and no crossing
                             }
                             // event_counts (:404): 1 below twice the denominator (exact), else the quotient
                             const bool big = cross && !(ad < fadd(den, den));
@@ -826,52 +1003,82 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                             const SpFrameEv ev = s_ev[n];
                             const bool gate = s_g[n].gate != 0;
                             const float C = up ? pos : neg;
-                            // iteration 0 passes and none after it does (with the gate on nothing
-                            // passes within Tr of it: the last iteration, c-1, decides)
-                            bool simple = !bit && ev.mxf >= 1.f;
-                            if (gate) {
-                                simple = simple && fsub(ev.ts1, tm) > Tr;
-                                if (big) {
-                                    const float tc = fadd(ev.t0, fmul(ev.step, fminf(cntf, ev.mxf)));
-                                    simple = simple && !(fsub(tc, ev.ts1) > Tr);
-                                }
-                            } else {
-                                simple = simple && !big;
-                            }
                             SpEv1 r;
-                            r.one = simple; r.slow = false; r.first = true; r.ts = ev.ts1;
-                            if (!simple) r = sp_classify(ev, gate, cntf, bit, tm, Tr);
+                            r.one = false; r.slow = false; r.first = true; r.ts = ev.ts1;
+                            bool simple = false;
+                            if (cross || bit) {
+                                // iteration 0 passes and none after it does (with the gate on nothing
+                                // passes within Tr of it: the last iteration, c-1, decides)
+                                simple = !bit && ev.mxf >= 1.f;
+                                if (gate) {
+                                    simple = simple && fsub(ev.ts1, tm) > Tr;
+                                    if (big) {
+                                        const float tc = fadd(ev.t0, fmul(ev.step, fminf(cntf, ev.mxf)));
+                                        simple = simple && !(fsub(tc, ev.ts1) > Tr);
+                                    }
+                                } else {
+                                    simple = simple && !big;
+                                }
+                                r.one = simple;
+                                if (!simple) r = sp_classify(ev, gate, cntf, bit, tm, Tr);
+                            }
 #ifdef SP_EXP_STAMPS
                             if (tl && pass == kSpPre)
                                 atomicAdd((unsigned long long*)&tl[24], r.slow ? (bit ? 1ull : (1ull << 16)) : (simple ? (1ull << 48) : (1ull << 32)));
 #endif
                             if (r.slow) {
-                                SP_SLOW_FRAME(n, cntf, up, C, bit);
-                            } else if (r.one) {
-                                // exactly one event, at ts (:478-502); pol * w is w or -w
-                                if (gate) tm = r.ts;
-                                const float bbf = r.first ? ev.bbf : floorf(r.ts);
-                                float wr = r.first ? ev.wr : fsub(r.ts, bbf);
-                                float wl = r.first ? ev.wl : fsub(1.0f, wr);
-                                if (!up) { wl = -wl; wr = -wr; }
-                                if (bbf == 0.f) { v0 = fadd(v0, wl); v1 = fadd(v1, wr); }
-                                else if (bbf == 1.f) { v1 = fadd(v1, wl); v2 = fadd(v2, wr); }
-                                else if (bbf == 2.f) { v2 = fadd(v2, wl); v3 = fadd(v3, wr); }
-                                else if (bbf == 3.f) { v3 = fadd(v3, wl); v4 = fadd(v4, wr); }
-                                else if (bbf == 4.f) { v4 = fadd(v4, wl); }
-                                base = fadd(base, up ? C : -C);   // :522: (pol * 1) * C
-                                nev += 1u;
+                                // (a pending shot event goes through the generic code with the rest)
+                                if (xts >= 0.f) SP_SHOT_FRAME(n, cntf, up, C, fI, fu);
+                                else SP_SLOW_FRAME(n, cntf, up, C, bit);
+                            } else {
+                                const float base_pre = base;
+                                if (r.one) {
+                                    // exactly one event, at ts (:478-502); pol * w is w or -w
+                                    if (gate) tm = r.ts;
+                                    const float bbf = r.first ? ev.bbf : floorf(r.ts);
+                                    float wr = r.first ? ev.wr : fsub(r.ts, bbf);
+                                    float wl = r.first ? ev.wl : fsub(1.0f, wr);
+                                    if (!up) { wl = -wl; wr = -wr; }
+                                    if (bbf == 0.f) { v0 = fadd(v0, wl); v1 = fadd(v1, wr); }
+                                    else if (bbf == 1.f) { v1 = fadd(v1, wl); v2 = fadd(v2, wr); }
+                                    else if (bbf == 2.f) { v2 = fadd(v2, wl); v3 = fadd(v3, wr); }
+                                    else if (bbf == 3.f) { v3 = fadd(v3, wl); v4 = fadd(v4, wr); }
+                                    else if (bbf == 4.f) { v4 = fadd(v4, wl); }
+                                    base = fadd(base, up ? C : -C);   // :522: (pol * 1) * C
+                                    nev += 1u;
+                                }
+                                if (xts >= 0.f && (!gate || fsub(xts, tm) > Tr)) {
+                                    // the shot event, after the pixel's own (:449-502 at a later iteration)
+                                    if (gate) tm = xts;
+                                    const float xb = floorf(xts);
+                                    float xr = fsub(xts, xb);
+                                    float xl = fsub(1.0f, xr);
+                                    if (!up) { xl = -xl; xr = -xr; }
+                                    if (xb == 0.f) { v0 = fadd(v0, xl); v1 = fadd(v1, xr); }
+                                    else if (xb == 1.f) { v1 = fadd(v1, xl); v2 = fadd(v2, xr); }
+                                    else if (xb == 2.f) { v2 = fadd(v2, xl); v3 = fadd(v3, xr); }
+                                    else if (xb == 3.f) { v3 = fadd(v3, xl); v4 = fadd(v4, xr); }
+                                    else if (xb == 4.f) { v4 = fadd(v4, xl); }
+                                    // :522 with final = 1 or 2: (pol * final) * C, 2C being exact
+                                    const float st = r.one ? fadd(C, C) : C;
+                                    base = fadd(base_pre, up ? st : -st);
+                                    nev += 1u;
+                                }
                             }
                             ++n;
                         }
                     }
                 }
 #ifdef SP_EXP_STAMPS
-                if (tl && pass == kSpPre && lane == 0) {
-                    const long long now = fx_now();
-                    if (t == 0) tl[17] = now;
-                    if (t == th) tl[19] = now;
-                    if (t == th + tc - 1) tl[21] = now;
+                if (tl && pass == kSpPre) {
+                    // the longest task of the round: duration, queue index, time in generic calls
+                    for (int o = 16; o > 0; o >>= 1) slow_t = max(slow_t, __shfl_xor_sync(0xffffffffu, slow_t, o));
+                    if (lane == 0) {
+                        const unsigned long long d = (unsigned long long)(fx_now() - task_t0);
+                        atomicMax((unsigned long long*)&tl[16], (d << 32) | ((unsigned long long)(slow_t >> 4) << 8) | (unsigned)t);
+                        tl[17] = th; tl[18] = tc;
+                        if (t == 0) tl[19] = fx_now();
+                    }
                 }
 #endif
                 if (on) {
