@@ -225,6 +225,47 @@ def test_forward_clip_equals_pack_loop(fdt):
     np.testing.assert_array_equal(a[3], b[3])
 
 
+@pytest.mark.parametrize("noise", ["philox", "off"])
+def test_forward_clip_chained_launches(noise):
+    """A long clip goes out as chains (one launch of the specialised fixed-point kernel for up to
+    16 consecutive packs, v2e_clip_forward): results, per-pack event counts and the carried state
+    must equal the per-pack loop bit for bit, the launch count must show the chains, and the event
+    intervals must add up to the clip's device time."""
+    from v2e2v_b200 import _cabi
+    cfg, H, W, T, K = dict(gc.CFG2), 180, 240, 10, 24
+    if noise == "off":
+        cfg.update(leak_rate_hz=0, shot_noise_rate_hz=0)
+    pos, neg, nra = gc.make_planes(29, H, W, cfg)
+    vids = [(fr.cuda(), tfr) for _, fr, tfr in gc.video(12, K, T, H, W)]
+    res = []
+    for clip in (False, True):
+        em = gc.cuda_emulator(cfg, "fixpoint", noise_mode=noise)
+        em.philox_seed = 7
+        em.set_planes(pos, neg, nra)
+        n0 = _cabi.lib().v2e_launch_count()
+        if clip:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K)]
+            vox, nev = em.forward_clip([v[0] for v in vids], [v[1] for v in vids], events=ev)
+            em.check_status()
+            torch.cuda.synchronize()
+            nev = nev.tolist()
+            launches = _cabi.lib().v2e_launch_count() - n0
+            assert launches <= 6, launches      # chunks of 1, 2, 4, 8, 9 packs
+            spans = [ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(K)]
+            assert all(x >= 0 for x in spans)
+            total = ev[0].elapsed_time(ev[2 * K - 1])
+            assert sum(spans) <= total * 1.001 + 1e-3
+        else:
+            outs = [em(fr, tfr) for fr, tfr in vids]
+            vox, nev = torch.cat([o[0] for o in outs]), [o[1] for o in outs]
+        res.append((vox.cpu().numpy(), nev, em.base_log_frame.cpu().numpy(),
+                    em.lp_log_frame0.cpu().numpy(), em.timestamp_mem.cpu().numpy(), em.t_previous))
+    a, b = res
+    assert a[1] == b[1] and a[5] == b[5]
+    for i in (0, 2, 3, 4):
+        np.testing.assert_array_equal(a[i], b[i])
+
+
 @pytest.mark.parametrize("engine", ["auto", "persistent", "stepwise"])
 def test_batch_of_sequences_equals_one_by_one(engine):
     """EventEmulatorBatch (S sequences per launch, BASELINE configs[3] geometry) == S separate

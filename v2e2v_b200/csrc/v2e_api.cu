@@ -168,7 +168,41 @@ int v2e_clip_forward(const v2e_config* c, const v2e_pack* packs, int n_packs, vo
                      size_t workspace_bytes, void* stream, void* const* events) {
     if (!packs || n_packs < 1) return V2E_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int i = 0; i < n_packs; ++i) {
+    // Chains: when the fixed-point engine's specialised kernel serves the request, up to
+    // V2E_MAX_SEQ_PER_LAUNCH consecutive packs go out as ONE launch (the kernel loops over the
+    // packs; no launch gap, no set-up in between).  The first pack's event pair then brackets the
+    // whole launch and the other pairs of the chain are empty intervals after it, so that the
+    // intervals still add up to the device time of the clip.
+    static const bool no_chain = getenv("V2E_NO_CHAIN") != nullptr;   // development aid
+    CfgDev cfg;
+    int i0 = 0;
+    if (!no_chain && n_packs > 1 && make_cfg(c, cfg) == V2E_OK && workspace && aligned16(workspace) &&
+        workspace_bytes >= step_layout(cfg, 1).total && v2e_resolve_engine(c, 1) == V2E_ENGINE_FIXPOINT) {
+        const int rounds = c->philox_rounds == 7 ? 7 : 10;
+        while (n_packs - i0 > 1) {
+            const int m = n_packs - i0 < V2E_MAX_SEQ_PER_LAUNCH ? n_packs - i0 : V2E_MAX_SEQ_PER_LAUNCH;
+            const int T = packs[i0].sc.num_frames;
+            bool ok = T >= 2 && T <= V2E_MAX_FRAMES;
+            for (int j = 0; ok && j < m; ++j) ok = check_pack(cfg, packs[i0 + j], T) == V2E_OK;
+            if (!ok) break;   // (the per-pack path reports what is wrong)
+            if (events && events[2 * i0]) {
+                const int rc = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i0], st));
+                if (rc != V2E_OK) return rc;
+            }
+            const int rc = run_fixpoint(cfg, c->frame_dtype, rounds, packs + i0, 1, workspace, st, m);
+            if (rc == V2E_ERR_UNSUPPORTED) break;   // nothing was enqueued: one launch per pack below
+            if (rc != V2E_OK) return rc;
+            if (events)
+                for (int j = 0; j < m; ++j) {
+                    void* const e1 = events[2 * (i0 + j) + 1];
+                    void* const e0 = j + 1 < m ? events[2 * (i0 + j + 1)] : nullptr;
+                    if (e1 && cuda_ok(cudaEventRecord((cudaEvent_t)e1, st)) != V2E_OK) return V2E_ERR_CUDA;
+                    if (e0 && cuda_ok(cudaEventRecord((cudaEvent_t)e0, st)) != V2E_OK) return V2E_ERR_CUDA;
+                }
+            i0 += m;
+        }
+    }
+    for (int i = i0; i < n_packs; ++i) {
         if (events && events[2 * i]) {
             const int rc = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i], st));
             if (rc != V2E_OK) return rc;

@@ -770,15 +770,31 @@ static int launch_fixpoint(const FxParams& prm, const FxPlan& pl, cudaStream_t s
     return launch_fixpoint_v<FDT, R, NOISE, CUTOFF, false>(prm, pl, st);
 }
 
+// n_chain > 1: packs[0..n_chain) are consecutive packs of ONE sequence (n_seq == 1), served by one
+// launch of the specialised kernel; V2E_ERR_UNSUPPORTED (before anything is enqueued) when the
+// request does not qualify - the caller then launches them one by one.
 template <int FDT>
 static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, int n_seq,
-                          void* workspace, cudaStream_t st) {
+                          void* workspace, cudaStream_t st, int n_chain) {
     const FxPlan pl = fx_plan(cfg, n_seq, packs[0].sc.num_frames);
     if (!pl.ok) return V2E_ERR_UNSUPPORTED;
+    const int n_blk = n_chain > 1 ? n_chain : n_seq;
+    if (n_chain > 1) {
+        if (n_seq != 1 || n_chain > V2E_MAX_SEQ_PER_LAUNCH || !pl.spec) return V2E_ERR_UNSUPPORTED;
+        for (int s = 0; s < n_chain; ++s) {
+            const v2e_pack& p = packs[s];
+            if (p.sc.num_frames != packs[0].sc.num_frames || p.base_log_frame != packs[0].base_log_frame ||
+                p.lp_log_frame0 != packs[0].lp_log_frame0 || p.timestamp_mem != packs[0].timestamp_mem || p.pos_thres != packs[0].pos_thres ||
+                p.neg_thres != packs[0].neg_thres || p.noise_rate != packs[0].noise_rate ||
+                p.dbg_pol || p.dbg_cnt || p.dbg_final || p.dbg_leak_randn || p.dbg_shot)
+                return V2E_ERR_UNSUPPORTED;
+        }
+    }
     static thread_local FxParams prm;
     const StepLayout lay = step_layout(cfg, n_seq);
     prm.cfg = cfg;
     prm.n_seq = n_seq;
+    prm.n_chain = n_chain > 1 ? n_chain : 1;
     prm.tiles_per_seq = pl.tiles_per_seq;
     prm.tile_px = pl.tile_px;
     prm.cap = pl.cap;
@@ -794,24 +810,13 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     bool dbg = false;
     static thread_local FxSeqBlock stage[V2E_MAX_SEQ_PER_LAUNCH];
     static thread_local unsigned ring_pos = 0;
-    for (int s = 0; s < n_seq; ++s) {
-        FxSeqBlock& b = n_seq == 1 ? prm.one : stage[s];
+    for (int s = 0; s < n_blk; ++s) {
+        FxSeqBlock& b = n_blk == 1 ? prm.one : stage[s];
         fill_seq(b.sq, packs[s]);
         for (int n = 1; n < packs[s].sc.num_frames; ++n)
             b.fr[n] = make_frame_sc(cfg, packs[s].sc.fr[n]);
         const v2e_pack& p = packs[s];
         dbg = dbg || p.dbg_pol || p.dbg_cnt || p.dbg_final || p.dbg_leak_randn || p.dbg_shot;
-    }
-    prm.blocks = nullptr;
-    if (n_seq > 1) {
-        // the records of a multi-sequence launch go through the workspace, copied in stream order
-        // (a ring of slots: the copy for launch i+1 never touches what launch i is reading)
-        FxSeqBlock* slot = (FxSeqBlock*)((char*)workspace + lay.fxblk_off) +
-                           (size_t)(ring_pos++ % kFxBlkRing) * V2E_MAX_SEQ_PER_LAUNCH;
-        const int rc = cuda_ok(cudaMemcpyAsync(slot, stage, sizeof(FxSeqBlock) * n_seq,
-                                               cudaMemcpyHostToDevice, st));
-        if (rc != V2E_OK) return rc;
-        prm.blocks = slot;
     }
     const bool leak = cfg.leak_on && cfg.noise_mode != V2E_NOISE_OFF;
     const bool shot = cfg.shot_on && cfg.noise_mode != V2E_NOISE_OFF;
@@ -820,6 +825,18 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     if (!dbg) {
         if (!leak && !shot) noise = 0;
         else if (philox && leak && shot) noise = 1;
+    }
+    if (n_chain > 1 && noise == 2) return V2E_ERR_UNSUPPORTED;   // (nothing has been enqueued yet)
+    prm.blocks = nullptr;
+    if (n_blk > 1) {
+        // the records of a multi-sequence launch or a chain go through the workspace, copied in stream order
+        // (a ring of slots: the copy for launch i+1 never touches what launch i is reading)
+        FxSeqBlock* slot = (FxSeqBlock*)((char*)workspace + lay.fxblk_off) +
+                           (size_t)(ring_pos++ % kFxBlkRing) * V2E_MAX_SEQ_PER_LAUNCH;
+        const int rc = cuda_ok(cudaMemcpyAsync(slot, stage, sizeof(FxSeqBlock) * n_blk,
+                                               cudaMemcpyHostToDevice, st));
+        if (rc != V2E_OK) return rc;
+        prm.blocks = slot;
     }
 #ifdef V2E_FX_DEV   // development builds: one Philox depth only (fewer instantiations to compile)
 #define FX_BY_ROUNDS(N, C) launch_fixpoint<FDT, 10, N, C>(prm, pl, st)
@@ -837,15 +854,15 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
 }
 
 int run_fixpoint(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs, int n_seq,
-                 void* workspace, cudaStream_t st) {
+                 void* workspace, cudaStream_t st, int n_chain) {
     switch (frame_dtype) {
 #ifndef V2E_FX_DEV
-        case V2E_DT_U8: return run_fixpoint_t<V2E_DT_U8>(cfg, rounds, packs, n_seq, workspace, st);
-        case V2E_DT_BF16: return run_fixpoint_t<V2E_DT_BF16>(cfg, rounds, packs, n_seq, workspace, st);
+        case V2E_DT_U8: return run_fixpoint_t<V2E_DT_U8>(cfg, rounds, packs, n_seq, workspace, st, n_chain);
+        case V2E_DT_BF16: return run_fixpoint_t<V2E_DT_BF16>(cfg, rounds, packs, n_seq, workspace, st, n_chain);
 #else
         case V2E_DT_U8: case V2E_DT_BF16: return V2E_ERR_UNSUPPORTED;
 #endif
-        default: return run_fixpoint_t<V2E_DT_F32>(cfg, rounds, packs, n_seq, workspace, st);
+        default: return run_fixpoint_t<V2E_DT_F32>(cfg, rounds, packs, n_seq, workspace, st, n_chain);
     }
 }
 

@@ -65,7 +65,8 @@ struct FxParams {
     float* spill_vox;      // [n_seq][nb][P] voxel accumulators of spilled pixels
     float* spill_state;    // [n_seq][3][P]  base, lp, tmem results of spilled pixels
     long long* timeline;   // development aid (V2E_TIMELINE=1): [cta][32] globaltimer stamps
-    const FxSeqBlock* blocks;   // n_seq > 1: records in the workspace (copied there in stream order)
+    int n_chain;       // consecutive packs of the one sequence served by this launch (n_seq == 1), else 1
+    const FxSeqBlock* blocks;   // n_seq > 1 or a chain: records in the workspace (copied there in stream order)
     FxSeqBlock one;             // n_seq == 1: the record travels with the parameters
 };
 static_assert(sizeof(FxParams) < 4000, "keep the kernel parameters on the fast launch path");

@@ -293,8 +293,14 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seq = blockIdx.x / prm.tiles_per_seq;
     const int tile = blockIdx.x - seq * prm.tiles_per_seq;
-    // this sequence's launch record -> shared memory
-    const FxSeqBlock* blk = prm.blocks ? prm.blocks + seq : &prm.one;
+    // A launch serves one pack of n_seq sequences, or a chain of n_chain consecutive packs of one
+    // sequence (the caller's pack loop, test.py:115-121, in one launch: every CTA keeps its tile,
+    // the state planes carry over in place, and neither the launch gap nor the set-up is paid
+    // again).  Consecutive packs of a chain alternate between two sets of barrier words, so that
+    // the last CTA to leave a pack can zero its set while the others are already in the next.
+    for (int pk = 0; pk < prm.n_chain; ++pk) {
+    // this pack's launch record -> shared memory
+    const FxSeqBlock* blk = prm.blocks ? prm.blocks + seq + pk : &prm.one;
     {
         unsigned* d_sq = (unsigned*)(smem_raw + 3840);
         const unsigned* s_sq = (const unsigned*)&blk->sq;
@@ -305,7 +311,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     }
     __syncthreads();
     const SeqDev& sq = *(const SeqDev*)(smem_raw + 3840);
-    FxWork& fx = prm.fx[seq];
+    FxWork& fx = prm.fx[seq + (pk & 1)];
+    FxWork& fx0 = prm.fx[seq];   // holds the hint for the launch that follows
     const int P = cfg.P;
     const bool normalise = cfg.output_mode == V2E_OUT_VOXEL;
 
@@ -341,8 +348,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     __syncthreads();
     FX_STAMP(0);
     if (prm.timeline && blockIdx.x == 0 && tid == 0)
-        prm.timeline[160 * 32 + 2 * (fx.pad[0] & 127u)] = fx_now();
-    load_lut(s_lut, cfg.lut);
+        prm.timeline[160 * 32 + 2 * (fx0.pad[0] & 127u)] = fx_now();
+    if (pk == 0) load_lut(s_lut, cfg.lut);
     auto set_globals = [&](int n, int mx) {
         const FrameGlobals g = frame_globals(mx, sq.duration, sq.Tr);
         s_g[n] = g;
@@ -364,7 +371,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     };
     if (tid < V2E_MAX_FRAMES) {
         // the guess: last pack's maxima (a hint kept in the workspace; any value is correct)
-        const unsigned h = fx.guess[tid];
+        // (later packs of a chain: the maxima every CTA gathered at the end of the last one)
+        const unsigned h = pk == 0 ? fx0.guess[tid] : (tid < T ? s_gmax[tid] + 1u : 0u);
         if (tid < T) set_globals(tid, h ? (int)h - 1 : 8);
         s_max[tid] = 0;
         s_gmax[tid] = 0;
@@ -1247,9 +1255,9 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     if (tile == 0 && tid >= 1 && tid < V2E_MAX_FRAMES) {
         if (tid < T) {
             if (sq.max_iters) sq.max_iters[tid] = (int)s_gmax[tid];
-            fx.guess[tid] = s_gmax[tid] + 1u;
+            if (pk == prm.n_chain - 1) fx0.guess[tid] = s_gmax[tid] + 1u;
         } else {
-            fx.guess[tid] = 0u;
+            if (pk == prm.n_chain - 1) fx0.guess[tid] = 0u;
         }
     }
     __syncthreads();
@@ -1328,11 +1336,13 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
             fx.exit_count = 0;
             fx.arrive = 0;
             if (prm.timeline && seq == 0) {
-                prm.timeline[160 * 32 + 2 * (fx.pad[0] & 127u) + 1] = fx_now();
-                prm.timeline[160 * 32 + 256 + (fx.pad[0] & 127u)] = pass + 1;   // rounds, pre-pass included
-                fx.pad[0] += 1;
+                prm.timeline[160 * 32 + 2 * (fx0.pad[0] & 127u) + 1] = fx_now();
+                prm.timeline[160 * 32 + 256 + (fx0.pad[0] & 127u)] = pass + 1;   // rounds, pre-pass included
+                fx0.pad[0] += 1;
             }
         }
+    }
+    __syncthreads();   // (the next pack of the chain re-initialises the header)
     }
 }
 
