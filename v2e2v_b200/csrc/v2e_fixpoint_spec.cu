@@ -212,6 +212,22 @@ __device__ __forceinline__ SpEv1 sp_classify(const SpFrameEv& ev, bool gate, flo
     const bool more = nxt < cf && (!gate || fsub(tc, r.ts) > Tr);
     r.slow = bit || (any && ((!first && !est) || more));
     r.one = any && !r.slow;
+    if (r.slow && !bit && gate && any && !first && !est) {
+        // the estimate missed (rare): walk to the first iteration that passes, with the exact
+        // predicate - it exists (`any`: the last one passes) and the predicate is monotone
+        float j = 1.f;   // iteration index; iteration 0 was refused (`first`)
+        float ts = fadd(ev.t0, fmul(ev.step, 2.f));
+        while (j + 1.f < cf && !(fsub(ts, tm) > Tr)) {
+            j += 1.f;
+            ts = fadd(ev.t0, fmul(ev.step, j + 1.f));
+        }
+        // one more after it?  (the last iteration decides)
+        if (!(j + 1.f < cf && fsub(tc, ts) > Tr)) {
+            r.slow = false;
+            r.one = true;
+            r.ts = ts;
+        }
+    }
     return r;
 }
 
@@ -244,7 +260,52 @@ __device__ __forceinline__ bool sp_mark_data(const SeqDev& sq, const float2* s_l
 struct SpShot {
     int kind;
     float ts;
+    float g, p_it;   // iteration of the first firing and the per-iteration probability (kinds 1, 2 with ts >= 1)
 };
+
+// The iteration loop of a frame with shot firings, for the cases sp_shot_lean does not settle in
+// closed form (a second firing within the frame, events of the pixel's own that the refractory
+// gate does not reduce to one): iterate_pixel's shot_mode-2 walk over the iterations that can
+// carry an event - [0, cnt) and the firings - under the same preconditions as sp_shot_lean
+// (p_it < 1e-3, at most 24 iterations: a follow-up uniform >= 0.03 puts the next firing beyond the
+// frame without forming the logarithms).  Small and out of line: it runs a few times per pack, and
+// the generic fx_event_frame / fx_events pair costs microseconds of instruction fetch each time.
+// Returns (final << 32) | bits(timestamp_mem); voxel accumulators at vp[b * vstride].
+template <int R>
+static __device__ __noinline__ unsigned long long sp_shot_loop(unsigned long long ctr, int n, int p,
+                                                               float t0, float step, float Tr, int gate,
+                                                               int mx, int cnt, int first_shot, float p_it,
+                                                               float pol, float tm, float* vp, int vstride) {
+    int next = first_shot, fin = 0;
+    unsigned follow = 2;
+    for (int i = cnt == 0 ? next : 0; i < mx;) {
+        const int cur = i;
+        bool m = cnt >= i + 1;
+        if (i == next) {
+            m = true;
+            const uint4 w = noise_words<R>(ctr, (unsigned)n, (unsigned)p, follow);
+            follow = follow < 0x7fu ? follow + 1 : follow;
+            const float u2 = (float)(w.x >> 8) * (1.0f / 16777216.0f);
+            next = 0x3fffffff;
+            if (u2 < 0.03f) next = i + 1 + (int)fminf(geometric_skip_small(u2, p_it), 1.0e9f);
+        }
+        i = cur + 1;
+        if (i >= cnt && i < next) i = next;
+        const float ts = fadd(t0, fmul(step, (float)(cur + 1)));
+        if (gate) {   // v2e_model.py:469-472
+            m = fsub(m ? ts : 0.f, tm) > Tr;
+            if (m) tm = ts;
+        }
+        if (!m) continue;
+        fin += 1;
+        const float ti = floorf(ts);   // v2e_model.py:478-502
+        const float d = fsub(ts, ti);
+        const int b = (int)ti;
+        if (b >= 0 && b < kFxSpecNb) vp[(size_t)b * vstride] = fadd(vp[(size_t)b * vstride], fmul(pol, fsub(1.0f, d)));
+        if (b >= 0 && b + 1 < kFxSpecNb) vp[(size_t)(b + 1) * vstride] = fadd(vp[(size_t)(b + 1) * vstride], fmul(pol, d));
+    }
+    return ((unsigned long long)(unsigned)fin << 32) | (unsigned long long)__float_as_uint(tm);
+}
 template <int R>
 __device__ __forceinline__ SpShot sp_shot_lean(const CfgDev& cfg, const SeqDev& sq, double sa, bool f64,
                                                const SpFrameEv& ev, int n, int p, bool up, float C,
@@ -252,6 +313,8 @@ __device__ __forceinline__ SpShot sp_shot_lean(const CfgDev& cfg, const SeqDev& 
     SpShot r;
     r.kind = 2;
     r.ts = 0.f;
+    r.g = 0.f;
+    r.p_it = 0.f;
     if (!(ev.mxf >= 1.f) || !(ev.mxf <= 24.f)) return r;
     const float fac = fadd(fmul(cfg.shot_inten_m1, I), 1.0f);
     const float pp = fmul(up ? cfg.rn_pos : cfg.rn_neg, C);
@@ -264,6 +327,9 @@ __device__ __forceinline__ SpShot sp_shot_lean(const CfgDev& cfg, const SeqDev& 
         r.kind = 0;
         return r;
     }
+    r.g = g;
+    r.p_it = p_it;
+    r.ts = 1.f;
     // the next firing, from a fresh uniform (drawn when the loop reaches the first one).  It lies
     // beyond the frame whenever the uniform is not tiny: log1p(-0.03) / log1p(-p) > 30 iterations
     // for p < 1e-3 and a frame has at most 24 here, so those logarithms are never formed.
@@ -846,6 +912,23 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         nev += (unsigned)fin_;                                                                         \
         SP_T1                                                                                          \
     } while (0)
+                // the same frame through the small shot loop (first firing and probability known)
+#define SP_SHOT_LOOP(n_, cntf_, up_, C_, gfirst_, pit_)                                                 \
+    do {                                                                                               \
+        SP_T0                                                                                          \
+        float* vp_ = (float*)(ep + FX_V0 * cap);                                                       \
+        vp_[0] = v0; vp_[cap] = v1; vp_[2 * cap] = v2; vp_[3 * cap] = v3; vp_[4 * cap] = v4;           \
+        const FrameGlobals g_ = s_g[(n_)];                                                             \
+        const unsigned long long r_ = sp_shot_loop<R>(                                                 \
+            sq.philox_ctr, (n_), p, s_fr[(n_)].t_bin_prev, g_.ts_step, Tr, g_.gate, g_.mx,             \
+            min((int)(cntf_), g_.mx), (int)(gfirst_), (pit_), (up_) ? 1.f : -1.f, tm, vp_, cap);       \
+        const int fin_ = (int)(r_ >> 32);                                                              \
+        tm = __uint_as_float((unsigned)r_);                                                            \
+        v0 = vp_[0]; v1 = vp_[cap]; v2 = vp_[2 * cap]; v3 = vp_[3 * cap]; v4 = vp_[4 * cap];           \
+        if (fin_) base = fadd(base, fmul(fmul((up_) ? 1.f : -1.f, (float)fin_), (C_))); /* :522 */     \
+        nev += (unsigned)fin_;                                                                         \
+        SP_T1                                                                                          \
+    } while (0)
                 const bool shot_data = SHOT && (meta & kSpShotData);
                 const float shot_I = shot_data ? __uint_as_float(ep[FX_SI * cap]) : 0.f;
                 const float shot_u = shot_data ? __uint_as_float(ep[FX_SU * cap]) : 0.f;
@@ -897,7 +980,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
 #ifdef SP_EXP_STAMPS
                                     if (tl && pass == kSpPre) atomicAdd((unsigned long long*)&tl[20], 1ull << (16 * (sh.kind == 2 ? (int)sh.ts : 1)));
 #endif
-                                    SP_SHOT_FRAME(n, cntf, up, C, fI, fu);
+                                    if (sh.kind == 2 && sh.ts < 1.f) SP_SHOT_FRAME(n, cntf, up, C, fI, fu);
+                                    else SP_SHOT_LOOP(n, cntf, up, C, sh.g, sh.p_it);
                                 }
                             }
                             if (r.slow) {
@@ -974,6 +1058,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                         if (n < T) {
                             const bool cross = ad >= den;
                             float xts = -1.f;   // stamp of a shot event that follows the pixel's own events
+                            float xg = 0.f, xp = 0.f;   // ... its iteration and the per-iteration probability
                             float fI = shot_I, fu = shot_u;
                             bool have = bit && shot_data;
                             if (bit && !shot_data && !(meta & 0x20000u))
@@ -993,11 +1078,12 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
 #ifdef SP_EXP_STAMPS
                                         if (tl && pass == kSpPre) atomicAdd((unsigned long long*)&tl[20], (1ull << (16 * (int)sh.ts)) << 8);
 #endif
-                                        SP_SHOT_FRAME(n, cq, up, C, fI, fu);
+                                        if (sh.ts < 1.f) SP_SHOT_FRAME(n, cq, up, C, fI, fu);
+                                        else SP_SHOT_LOOP(n, cq, up, C, sh.g, sh.p_it);
                                         ++n;
                                         continue;
                                     }
-                                    if (sh.kind == 1) xts = sh.ts;
+                                    if (sh.kind == 1) { xts = sh.ts; xg = sh.g; xp = sh.p_it; }
                                     // (kind 0: as if unmarked)
                                 }
                                 bit = false;
@@ -1036,7 +1122,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
 #endif
                             if (r.slow) {
                                 // (a pending shot event goes through the generic code with the rest)
-                                if (xts >= 0.f) SP_SHOT_FRAME(n, cntf, up, C, fI, fu);
+                                if (xts >= 0.f) SP_SHOT_LOOP(n, cntf, up, C, xg, xp);
                                 else SP_SLOW_FRAME(n, cntf, up, C, bit);
                             } else {
                                 const float base_pre = base;
