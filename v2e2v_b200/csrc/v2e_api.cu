@@ -185,11 +185,8 @@ int v2e_clip_forward(const v2e_config* c, const v2e_pack* packs, int n_packs, vo
             bool ok = T >= 2 && T <= V2E_MAX_FRAMES;
             for (int j = 0; ok && j < m; ++j) ok = check_pack(cfg, packs[i0 + j], T) == V2E_OK;
             if (!ok) break;   // (the per-pack path reports what is wrong)
-            if (events && events[2 * i0]) {
-                const int rc = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i0], st));
-                if (rc != V2E_OK) return rc;
-            }
-            const int rc = run_fixpoint(cfg, c->frame_dtype, rounds, packs + i0, 1, workspace, st, m);
+            const int rc = run_fixpoint(cfg, c->frame_dtype, rounds, packs + i0, 1, workspace, st, m,
+                                        events ? events[2 * i0] : nullptr);
             if (rc == V2E_ERR_UNSUPPORTED) break;   // nothing was enqueued: one launch per pack below
             if (rc != V2E_OK) return rc;
             if (events)

@@ -146,9 +146,10 @@ int run_runahead(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack*
 int persistent_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
 int runahead_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
 // n_chain > 1: one launch for n_chain consecutive packs of one sequence (V2E_ERR_UNSUPPORTED, with
-// nothing enqueued, when the request does not qualify)
+// nothing enqueued, when the request does not qualify); ev_launch: optional cudaEvent_t recorded
+// right before the kernel launch (after the launch records were copied)
 int run_fixpoint(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs, int n_seq,
-                 void* workspace, cudaStream_t st, int n_chain = 1);
+                 void* workspace, cudaStream_t st, int n_chain = 1, void* ev_launch = nullptr);
 int fixpoint_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
 
 }  // namespace v2e

@@ -35,6 +35,8 @@
 // non-integer frame values, packs longer than 11 frames) are "spilled": only their index is
 // kept, every pass re-reads their inputs from global memory and keeps their results in the
 // workspace until commit.  Slower, same results.
+#include <cstring>
+
 #include "v2e_fixpoint.cuh"
 
 namespace v2e {
@@ -775,7 +777,7 @@ static int launch_fixpoint(const FxParams& prm, const FxPlan& pl, cudaStream_t s
 // request does not qualify - the caller then launches them one by one.
 template <int FDT>
 static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, int n_seq,
-                          void* workspace, cudaStream_t st, int n_chain) {
+                          void* workspace, cudaStream_t st, int n_chain, void* ev_launch) {
     const FxPlan pl = fx_plan(cfg, n_seq, packs[0].sc.num_frames);
     if (!pl.ok) return V2E_ERR_UNSUPPORTED;
     const int n_blk = n_chain > 1 ? n_chain : n_seq;
@@ -828,6 +830,21 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     }
     if (n_chain > 1 && noise == 2) return V2E_ERR_UNSUPPORTED;   // (nothing has been enqueued yet)
     prm.blocks = nullptr;
+    prm.fr_in_params = n_blk == 1;
+    if (n_chain > 1) {
+        // a chain whose packs share the stream pass's frame scalars bit for bit (evenly spaced
+        // stamps: the usual case) keeps them in the kernel parameters, like a single pack
+        bool same = true;
+        for (int s = 1; same && s < n_chain; ++s)
+            for (int n = 1; same && n < packs[0].sc.num_frames; ++n)
+                same = memcmp(&stage[s].fr[n].s_large, &stage[0].fr[n].s_large, sizeof(float)) == 0 &&
+                       memcmp(&stage[s].fr[n].s_small, &stage[0].fr[n].s_small, sizeof(float)) == 0 &&
+                       memcmp(&stage[s].fr[n].sdt, &stage[0].fr[n].sdt, sizeof(float)) == 0;
+        if (same) {
+            for (int n = 1; n < packs[0].sc.num_frames; ++n) prm.one.fr[n] = stage[0].fr[n];
+            prm.fr_in_params = 1;
+        }
+    }
     if (n_blk > 1) {
         // the records of a multi-sequence launch or a chain go through the workspace, copied in stream order
         // (a ring of slots: the copy for launch i+1 never touches what launch i is reading)
@@ -837,6 +854,10 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
                                                cudaMemcpyHostToDevice, st));
         if (rc != V2E_OK) return rc;
         prm.blocks = slot;
+    }
+    if (ev_launch) {   // (timing aid: after the record copy, right before the kernel)
+        const int rc = cuda_ok(cudaEventRecord((cudaEvent_t)ev_launch, st));
+        if (rc != V2E_OK) return rc;
     }
 #ifdef V2E_FX_DEV   // development builds: one Philox depth only (fewer instantiations to compile)
 #define FX_BY_ROUNDS(N, C) launch_fixpoint<FDT, 10, N, C>(prm, pl, st)
@@ -854,15 +875,15 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
 }
 
 int run_fixpoint(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs, int n_seq,
-                 void* workspace, cudaStream_t st, int n_chain) {
+                 void* workspace, cudaStream_t st, int n_chain, void* ev_launch) {
     switch (frame_dtype) {
 #ifndef V2E_FX_DEV
-        case V2E_DT_U8: return run_fixpoint_t<V2E_DT_U8>(cfg, rounds, packs, n_seq, workspace, st, n_chain);
-        case V2E_DT_BF16: return run_fixpoint_t<V2E_DT_BF16>(cfg, rounds, packs, n_seq, workspace, st, n_chain);
+        case V2E_DT_U8: return run_fixpoint_t<V2E_DT_U8>(cfg, rounds, packs, n_seq, workspace, st, n_chain, ev_launch);
+        case V2E_DT_BF16: return run_fixpoint_t<V2E_DT_BF16>(cfg, rounds, packs, n_seq, workspace, st, n_chain, ev_launch);
 #else
         case V2E_DT_U8: case V2E_DT_BF16: return V2E_ERR_UNSUPPORTED;
 #endif
-        default: return run_fixpoint_t<V2E_DT_F32>(cfg, rounds, packs, n_seq, workspace, st, n_chain);
+        default: return run_fixpoint_t<V2E_DT_F32>(cfg, rounds, packs, n_seq, workspace, st, n_chain, ev_launch);
     }
 }
 

@@ -94,7 +94,8 @@ struct SpPx {   // one pixel after the frame loop
 
 // The frame loop of one pixel (v2e_model.py:321-322,332,350-404 up to the threshold test):
 // everything the frames present to the pixel whatever it does.
-// ONE: a single-sequence launch, whose per-frame scalars sit in the kernel parameters: they become
+// ONE: the stream pass's per-frame scalars sit in the kernel parameters (a single pack, or a chain
+// whose packs all have the same ones - evenly spaced stamps): they become
 // constant-bank operands of the arithmetic instead of a shared-memory load each.
 // SMALL: the pixel sits on the sensing-diversity grid (even row and column), a compile-time
 // choice so that the scalar is an operand and not a select.
@@ -1452,8 +1453,8 @@ static int launch_spec_1(const FxParams& prm, int grid, size_t smem, int optin, 
 
 template <int FDT, int R, int NOISE, bool CUTOFF>
 static int launch_spec_v(const FxParams& prm, int grid, size_t smem, int optin, cudaStream_t st) {
-    return prm.blocks ? launch_spec_1<FDT, R, NOISE, CUTOFF, false>(prm, grid, smem, optin, st)
-                      : launch_spec_1<FDT, R, NOISE, CUTOFF, true>(prm, grid, smem, optin, st);
+    return prm.fr_in_params ? launch_spec_1<FDT, R, NOISE, CUTOFF, true>(prm, grid, smem, optin, st)
+                            : launch_spec_1<FDT, R, NOISE, CUTOFF, false>(prm, grid, smem, optin, st);
 }
 
 template <int FDT>

@@ -359,18 +359,22 @@ class EventEmulator(nn.Module):
             if frames.dim() != 4:
                 raise ValueError("frames must be [num_packs, num_frames, height, width]")
             frames = list(frames.unbind(0))
-        flist = []
-        for fr in frames:
+        frames = list(frames)
+        K = len(frames)
+        if K < 1:
+            raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
+
+        def norm(fr):
+            # (per pack, inside the enqueue loop: the device starts on the first pack while the
+            # host is still looking at the others)
             if not fr.is_cuda:
                 raise RuntimeError("frames must be on the CUDA device (no CPU fallback)")
             if fr.dtype not in ops._FRAME_DT:
                 fr = fr.float()
             fr = fr.contiguous()
-            flist.append(fr.reshape(fr.shape[-3:]))
-        if not flist or any(f.shape != flist[0].shape or f.dtype != flist[0].dtype for f in flist):
-            raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
-        frames = flist
-        K = len(frames)
+            return fr.reshape(fr.shape[-3:])
+
+        frames[0] = norm(frames[0])
         num_frames, height, width = frames[0].shape
         if len(t_frames) != K:
             raise ValueError("need one stamp tensor per pack")
@@ -395,10 +399,14 @@ class EventEmulator(nn.Module):
         # growing chunks, so that the device works on chunk i while the host prepares chunk i+1.
         stream = torch.cuda.current_stream(dev).cuda_stream
         out_ptr, meta_ptr = out.data_ptr(), meta.data_ptr()
-        k0, chunk = 0, 1
-        while k0 < K:
+        k0, chunk, prev = 0, 1, 0     # chunks of 1, 1, 2, 3, 5, 8, 13, 16, 16, ... packs: the host
+        while k0 < K:                 # prepares a pack in about half the time the device needs for it
             k1 = min(K, k0 + chunk)
             for k in range(k0, k1):
+                if k:
+                    frames[k] = norm(frames[k])
+                    if frames[k].shape != frames[0].shape or frames[k].dtype != frames[0].dtype:
+                        raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
                 self._prep_pack(packs[k], frames[k], t_frames[k], out_ptr + k * ostride,
                                 meta_ptr + 16 * k)
             pk0 = C.cast(C.addressof(packs) + k0 * C.sizeof(_cabi.Pack), C.POINTER(_cabi.Pack))
@@ -408,7 +416,7 @@ class EventEmulator(nn.Module):
             rc = pl._lib.v2e_clip_forward(C.byref(pl.cfg), pk0, k1 - k0, self._workspace.data_ptr(),
                                           self._workspace.numel(), stream, ev0)
             _cabi.check(rc, "v2e_clip_forward")
-            k0, chunk = k1, min(2 * chunk, 16)
+            k0, chunk, prev = k1, min(chunk + prev if prev else 1, 16), chunk
         self._clip_keep = (frames, packs)       # keep the inputs alive until the stream is done
         self._last_meta = meta[-1]
         self._clip_meta = meta
