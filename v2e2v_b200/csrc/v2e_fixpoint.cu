@@ -842,6 +842,7 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
                        memcmp(&stage[s].fr[n].sdt, &stage[0].fr[n].sdt, sizeof(float)) == 0;
         if (same) {
             for (int n = 1; n < packs[0].sc.num_frames; ++n) prm.one.fr[n] = stage[0].fr[n];
+            prm.one.sq = stage[0].sq;   // (the planes of the sequence: the same for every pack)
             prm.fr_in_params = 1;
         }
     }

@@ -65,7 +65,7 @@ struct FxParams {
     float* spill_vox;      // [n_seq][nb][P] voxel accumulators of spilled pixels
     float* spill_state;    // [n_seq][3][P]  base, lp, tmem results of spilled pixels
     long long* timeline;   // development aid (V2E_TIMELINE=1): [cta][32] globaltimer stamps
-    int fr_in_params;  // one.fr holds the stream pass's frame scalars for every pack of this launch
+    int fr_in_params;  // one.fr and the plane pointers of one.sq are valid for every pack of this launch
     int n_chain;       // consecutive packs of the one sequence served by this launch (n_seq == 1), else 1
     const FxSeqBlock* blocks;   // n_seq > 1 or a chain: records in the workspace (copied there in stream order)
     FxSeqBlock one;             // n_seq == 1: the record travels with the parameters

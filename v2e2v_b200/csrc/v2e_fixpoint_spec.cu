@@ -378,6 +378,10 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     }
     __syncthreads();
     const SeqDev& sq = *(const SeqDev*)(smem_raw + 3840);
+    // what every pack of this launch shares (the sequence's planes) is read from the kernel
+    // parameters when they hold it (ONE): constant-bank operands instead of shared-memory loads
+    // that would be repeated after every table store
+    const SeqDev& sqc = ONE ? prm.one.sq : sq;
     FxWork& fx = prm.fx[seq + (pk & 1)];
     FxWork& fx0 = prm.fx[seq];   // holds the hint for the launch that follows
     const int P = cfg.P;
@@ -479,16 +483,16 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         const bool valid = c0 + 2 * lane < tile_n;
         const int l = min(c0 + 2 * lane, tile_n - 2);   // lanes past the end shadow the last pair
         const int p = tile_px0 + l;
-        const float2 pos2 = __ldg((const float2*)(sq.pos + p));
-        const float2 neg2 = __ldg((const float2*)(sq.neg + p));
+        const float2 pos2 = __ldg((const float2*)(sqc.pos + p));
+        const float2 neg2 = __ldg((const float2*)(sqc.neg + p));
         float2 nra2 = make_float2(0.f, 0.f), base2 = nra2, lp2 = nra2, tm2 = nra2, x02 = nra2;
-        if (LEAK) nra2 = __ldg((const float2*)(sq.nra + p));
+        if (LEAK) nra2 = __ldg((const float2*)(sqc.nra + p));
         if (sq.first_pack) {
             x02 = sp_load_frame2<FDT>(sq.frames, p);
         } else {
-            base2 = *(const float2*)(sq.base + p);
-            if (CUTOFF) lp2 = *(const float2*)(sq.lp + p);
-            tm2 = *(const float2*)(sq.tmem + p);
+            base2 = *(const float2*)(sqc.base + p);
+            if (CUTOFF) lp2 = *(const float2*)(sqc.lp + p);
+            tm2 = *(const float2*)(sqc.tmem + p);
         }
         float2 x2[kSpNF];
 #pragma unroll
@@ -588,25 +592,27 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
             // (the spill path recomputes a pixel from its stored state)
             if (CUTOFF) {
                 if (!spilled[0] && !spilled[1]) {
-                    *(float2*)(sq.lp + p) = make_float2(lp_out[0], lp_out[1]);
+                    *(float2*)(sqc.lp + p) = make_float2(lp_out[0], lp_out[1]);
                 } else {
-                    if (!spilled[0]) sq.lp[p] = lp_out[0];
-                    if (!spilled[1]) sq.lp[p + 1] = lp_out[1];
+                    if (!spilled[0]) sqc.lp[p] = lp_out[0];
+                    if (!spilled[1]) sqc.lp[p + 1] = lp_out[1];
                 }
             }
             // (an active pixel's words are written again by the commit; nothing reads them before)
             if (!spilled[0] && !spilled[1]) {
-                *(float2*)(sq.base + p) = make_float2(base_out[0], base_out[1]);
-                *(float2*)(sq.tmem + p) = make_float2(tm_out[0], tm_out[1]);
+                *(float2*)(sqc.base + p) = make_float2(base_out[0], base_out[1]);
+                *(float2*)(sqc.tmem + p) = make_float2(tm_out[0], tm_out[1]);
             } else {
-                if (quiet[0]) { sq.base[p] = base_out[0]; sq.tmem[p] = tm_out[0]; }
-                if (quiet[1]) { sq.base[p + 1] = base_out[1]; sq.tmem[p + 1] = tm_out[1]; }
+                if (quiet[0]) { sqc.base[p] = base_out[0]; sqc.tmem[p] = tm_out[0]; }
+                if (quiet[1]) { sqc.base[p + 1] = base_out[1]; sqc.tmem[p + 1] = tm_out[1]; }
             }
             // zero voxel columns; the commit overwrites those of the active pixels
+            // (the pointer is read once: a store through it could alias the record it comes from)
+            void* const vox = sq.voxel;
 #pragma unroll
             for (int b = 0; b < nb; ++b) {
-                if (cfg.voxel_bf16) *(unsigned*)((__nv_bfloat16*)sq.voxel + (size_t)b * P + p) = 0u;
-                else *(float2*)((float*)sq.voxel + (size_t)b * P + p) = make_float2(0.f, 0.f);
+                if (cfg.voxel_bf16) *(unsigned*)((__nv_bfloat16*)vox + (size_t)b * P + p) = 0u;
+                else *(float2*)((float*)vox + (size_t)b * P + p) = make_float2(0.f, 0.f);
             }
         }
     }
@@ -1355,7 +1361,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
             const unsigned* ep = s_ent + i;
             const unsigned meta = ep[FX_META * cap];
             const int p = tile_px0 + (int)ep[FX_IDX * cap];
-            sq.base[p] = __uint_as_float(ep[FX_OB * cap]);
+            sqc.base[p] = __uint_as_float(ep[FX_OB * cap]);
             float vv[nb];
             if (meta & kSpStatic) {
                 // static entries: the one event (if any) sits at its frame's first stamp
@@ -1374,9 +1380,9 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                         if (ev.bbf + 1.f == (float)b) vv[b] = fadd(0.f, wr);
                     }
                 }
-                sq.tmem[p] = tm;
+                sqc.tmem[p] = tm;
             } else {
-                sq.tmem[p] = __uint_as_float(ep[FX_OT * cap]);
+                sqc.tmem[p] = __uint_as_float(ep[FX_OT * cap]);
 #pragma unroll
                 for (int b = 0; b < nb; ++b) vv[b] = __uint_as_float(ep[(FX_V0 + b) * cap]);
             }

@@ -34,7 +34,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, ops
-from .host_scalars import TimeState, pack_scalars
+from .host_scalars import PackScalarPrep, TimeState, pack_scalars
 
 logger = logging.getLogger(__name__)
 
@@ -318,8 +318,12 @@ class EventEmulator(nn.Module):
             self._init(height, width)
             if ext:
                 self.pos_thres, self.neg_thres, self.noise_rate_array = keep
-        pack_scalars(t_frames, num_frames, self.num_bins, self._refractory_host, self.cutoff_hz,
-                     self.ql, self.qs, self.shot_noise_rate_hz, self._t_prev, first, out=pk.sc)
+        key = (num_frames, self.num_bins, float(self._refractory_host), float(self.cutoff_hz),
+               float(self.ql), float(self.qs), float(self.shot_noise_rate_hz))
+        prep = getattr(self, "_scalar_prep", None)
+        if prep is None or prep.key != key:
+            prep = self._scalar_prep = PackScalarPrep(*key)
+        prep.fill(t_frames, self._t_prev, first, pk.sc)
         self.t_previous = self._t_prev.value
         self.frame_counter += num_frames
         pk.frames = fr.data_ptr()
