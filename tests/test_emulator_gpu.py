@@ -225,6 +225,42 @@ def test_forward_clip_equals_pack_loop(fdt):
     np.testing.assert_array_equal(a[3], b[3])
 
 
+@pytest.mark.parametrize("fdt", [torch.float32, torch.uint8])
+def test_forward_host_equals_forward(fdt):
+    """forward_host (frames in pinned host memory, staged on a copy stream, frame 0 of the
+    steady-state packs not copied - it is never read, v2e_model.py:263,350) == forward on device
+    frames, bit for bit, over a reset in the middle."""
+    cfg, H, W, T, K = gc.CFG2, 96, 160, 10, 5
+    pos, neg, nra = gc.make_planes(31, H, W, cfg)
+    vids = [(fr.to(fdt), tfr) for _, fr, tfr in gc.video(14, K, T, H, W)]
+    res = []
+    for host in (False, True):
+        em = gc.cuda_emulator(cfg, "auto", noise_mode="philox")
+        em.philox_seed = 5
+        em.set_planes(pos, neg, nra)
+        outs = []
+        for rnd in range(2):
+            for fr, tfr in vids:
+                if host:
+                    # (the staging buffers keep a stale frame 0 for every pack but the first)
+                    h = fr.clone().pin_memory()
+                    outs.append(em.forward_host(h, tfr))
+                else:
+                    outs.append(em(fr.cuda(), tfr))
+            if rnd == 0:
+                em.reset()
+                em.set_planes(pos, neg, nra)
+        torch.cuda.synchronize()
+        res.append(([o[0].cpu().numpy() for o in outs], [int(o[1]) for o in outs],
+                    em.base_log_frame.cpu().numpy(), em.timestamp_mem.cpu().numpy()))
+    a, b = res
+    assert a[1] == b[1]
+    for x, y in zip(a[0], b[0]):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+
+
 @pytest.mark.parametrize("noise", ["philox", "off"])
 def test_forward_clip_chained_launches(noise):
     """A long clip goes out as chains (one launch of the specialised fixed-point kernel for up to

@@ -428,6 +428,46 @@ class EventEmulator(nn.Module):
         self.num_events = num_events
         return out, num_events
 
+    def forward_host(self, frames, t_frames):
+        """``forward`` for frames that live in HOST memory (extension; what a caller does with the
+        frames of a video reader, test.py:115-116: ``frames.to(device)`` then the emulator).
+
+        frames: CPU tensor [1, num_frames, H, W], float32 / uint8 / bfloat16, ideally pinned.
+        The pack is staged through two device buffers on a copy stream, so that the copy of pack
+        k+1 runs while the kernel of pack k does (with ``lazy_num_events`` nothing blocks the
+        host).  Frame 0 of every pack but the first after ``reset()`` is never read by the
+        emulator (v2e_model.py:263,350: the loops start at n = 1; the first pack takes its
+        initial state from frame 0, :325-327), so it is not copied: T-1 frames per pack cross the
+        bus.  Returns what ``forward`` returns.
+        """
+        if frames.is_cuda:
+            return self.forward(frames, t_frames)
+        if frames.dim() != 4 or frames.size(0) != 1:
+            raise ValueError("frames must be [batch_size=1, num_frames, height, width]")
+        if frames.dtype not in ops._FRAME_DT:
+            frames = frames.float()
+        dev = self._dev
+        st = getattr(self, "_host_stage", None)
+        if st is None or st["shape"] != tuple(frames.shape) or st["dtype"] != frames.dtype:
+            st = self._host_stage = {
+                "shape": tuple(frames.shape), "dtype": frames.dtype, "k": 0,
+                "buf": [torch.empty(frames.shape, dtype=frames.dtype, device=dev) for _ in range(2)],
+                "ready": [torch.cuda.Event() for _ in range(2)],
+                "freed": [torch.cuda.Event() for _ in range(2)],
+                "stream": torch.cuda.Stream(dev)}
+        b = st["k"] & 1
+        st["k"] += 1
+        lo = 0 if self.base_log_frame is None else 1
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st["stream"]):
+            st["stream"].wait_event(st["freed"][b])
+            st["buf"][b][:, lo:].copy_(frames[:, lo:], non_blocking=True)
+            st["ready"][b].record(st["stream"])
+        cur.wait_event(st["ready"][b])
+        out = self.forward(st["buf"][b], t_frames)
+        st["freed"][b].record(cur)
+        return out
+
     def forward(self, frames, t_frames):
         """Compute events based on a sequence of frames (v2e_model.py:290-536).
 
