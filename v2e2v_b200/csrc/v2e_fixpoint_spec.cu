@@ -1249,16 +1249,35 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
             }
             if (warp == 0) {
                 // one warp polls (a poller per tile in every CTA floods the L2 with requests)
+                // (a lane's words are loaded together, then checked: one L2 round trip per sweep,
+                // not one per word)
+                constexpr int kPer = (kRaMaxTiles + 31) / 32;
+                unsigned long long w[kPer];
+                const unsigned long long tag = (unsigned long long)(pass + 1);
+                int spins = 0;
+                while (true) {
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 0; j < kPer; ++j) {
+                        const int i = lane + 32 * j;
+                        w[j] = i < prm.tiles_per_seq ? fx_ld_relaxed64(slots + i) : (tag << 54);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kPer; ++j) ok = ok && (w[j] >> 54) == tag;
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    if (++spins > kFxSpin) {
+                        s_cnt[2] = 1;
+#pragma unroll
+                        for (int j = 0; j < kPer; ++j) if ((w[j] >> 54) != tag) w[j] = 0ull;
+                        break;
+                    }
+                }
                 unsigned m[kSpNF];
 #pragma unroll
-                for (int k = 0; k < kSpNF; ++k) m[k] = 0u;
-                for (int i = lane; i < prm.tiles_per_seq; i += 32) {
-                    unsigned long long w;
-                    int spins = 0;
-                    while (((w = fx_ld_relaxed64(slots + i)) >> 54) != (unsigned long long)(pass + 1))
-                        if (++spins > kFxSpin) { s_cnt[2] = 1; w = 0ull; break; }
+                for (int k = 0; k < kSpNF; ++k) {
+                    m[k] = 0u;
 #pragma unroll
-                    for (int k = 0; k < kSpNF; ++k) m[k] = max(m[k], (unsigned)(w >> (6 * k)) & 63u);
+                    for (int j = 0; j < kPer; ++j) m[k] = max(m[k], (unsigned)(w[j] >> (6 * k)) & 63u);
                 }
 #pragma unroll
                 for (int k = 0; k < kSpNF; ++k) {
