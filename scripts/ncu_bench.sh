@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: scripts/ncu_bench.sh <tag> [bench args]  -> gpurun_out/<tag>_{bench.json,launches.csv,chain.ncu-rep,chain_summary.txt}
 # (1) bench.py plain, (2) the ncu launch list of the same command, (3) one --set full capture of a
-# chained launch of the specialised kernel (the 9th launch: a chain of 8 packs in the warm-up clip).
+# chained launch of the specialised kernel (the 9th launch: a chain of 3 packs in the warm-up clip, whose chunks are 1, 1, 2, 3, 5, ... packs).
 tag=$1; shift
 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
