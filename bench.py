@@ -125,7 +125,7 @@ def stamps(k):
 
 # -----------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
-    from v2e2v_b200 import EventEmulator, _cabi
+    from v2e2v_b200 import EventEmulator, EventEmulatorBatch, _cabi
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     H, W, S, desc = WORKLOADS[args.workload]
@@ -135,9 +135,16 @@ def run_ours(args, rank, world, local_rank):
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     torch.manual_seed(rank)
     ems, packs = [], []
+    # S > 1: the sequences of a rank go out S per launch (EventEmulatorBatch: the same S
+    # reference-style emulators, CTAs grouped per sequence)
+    batch = None
+    if S > 1:
+        batch = EventEmulatorBatch(S, device=dev, noise_mode=args.noise, engine=args.engine,
+                                   philox_rounds=args.philox_rounds, lazy_num_events=True, **EMU)
     for s in range(S):
-        em = EventEmulator(device=dev, noise_mode=args.noise, engine=args.engine,
-                           philox_rounds=args.philox_rounds, lazy_num_events=True, **EMU)
+        em = batch[s] if batch is not None else EventEmulator(
+            device=dev, noise_mode=args.noise, engine=args.engine,
+            philox_rounds=args.philox_rounds, lazy_num_events=True, **EMU)
         ems.append(em)
         base = torch.rand(1, 1, H, W, device=dev, generator=gen) * 255
         seqp = []
@@ -146,6 +153,9 @@ def run_ours(args, rank, world, local_rank):
             seqp.append(fr)
         packs.append(seqp)
     pinned = [[p.cpu().pin_memory() for p in seqp] for seqp in packs]
+    # [S, T, H, W] per ring slot for the batched launches
+    bpacks = ([torch.cat([packs[s][r] for s in range(S)]) for r in range(ring)]
+              if batch is not None else None)
     lib = _cabi.lib()
 
     def barrier():
@@ -163,8 +173,10 @@ def run_ours(args, rank, world, local_rank):
     # ---- device-resident throughput ("value") -------------------------------------------------
     k = 0
     for _ in range(Wm):
-        for s in range(S):
-            ems[s](packs[s][k % ring], stamps(k))
+        if batch is not None:
+            batch(bpacks[k % ring], stamps(k).expand(S, -1))
+        else:
+            ems[0](packs[0][k % ring], stamps(k))
         k += 1
     barrier()
     sampler = ClockSampler(local_rank)
@@ -182,11 +194,14 @@ def run_ours(args, rank, world, local_rank):
             if events is None:      # one event per clip: where the time goes (stderr)
                 clip_ev.append((torch.cuda.Event(enable_timing=True), n, time.perf_counter()))
                 clip_ev[-1][0].record()
-            for s in range(S):
-                ems[s].forward_clip([packs[s][(kk + j) % ring] for j in range(n)],
-                                    [stamps(kk + j) for j in range(n)],
-                                    events=None if events is None else events[i:i + 2 * n])
-                i += 2 * n
+            evs = None if events is None else events[i:i + 2 * n]
+            if batch is not None:
+                batch.forward_clip([bpacks[(kk + j) % ring] for j in range(n)],
+                                   [stamps(kk + j) for j in range(n)], events=evs)
+            else:
+                ems[0].forward_clip([packs[0][(kk + j) % ring] for j in range(n)],
+                                    [stamps(kk + j) for j in range(n)], events=evs)
+            i += 2 * n
             kk += n
         return kk
 
@@ -202,8 +217,10 @@ def run_ours(args, rank, world, local_rank):
     k = run_clips(k, K)
     e1.record()
     barrier()
-    for em in ems:
-        em.check_status()
+    if batch is not None:
+        batch.check_status()
+    else:
+        ems[0].check_status()
     if rank == 0 and len(clip_ev) > 1:
         per = [clip_ev[j][0].elapsed_time(clip_ev[j + 1][0]) / clip_ev[j][1] * 1e3
                for j in range(len(clip_ev) - 1)]
@@ -216,13 +233,13 @@ def run_ours(args, rank, world, local_rank):
     # kernel durations for the roofline: the same launches again, each bracketed by CUDA events
     # on the launching stream (the events cost ~20 us per launch, so they stay out of `value`)
     KR = min(K, 200)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * KR * S)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * KR)]
     k = run_clips(k, KR, events=ev)
     barrier()
     # One interval per pack.  When v2e_clip_forward chains packs into one launch the first pack's
     # interval is the whole launch and the others are empty: a launch is a run of intervals that
     # starts at a non-empty one.
-    pack_ms = [ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(KR * S)]
+    pack_ms = [ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(KR)]
     launch_ms, launch_packs = [], []
     for d in pack_ms:
         if d > 0.01 or not launch_ms:
@@ -274,7 +291,9 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    algo_bytes = ALGO_BYTES_PER_PIXEL_PACK * H * W          # one launch = one pack of one sequence
+    # one timed interval = one step = one pack of each of the rank's S sequences (S = 1: one
+    # pack; S > 1: one batched launch)
+    algo_bytes = ALGO_BYTES_PER_PIXEL_PACK * H * W * S
     achieved = algo_bytes / (kern_pack_ms * 1e-3) / 1e9
     tkey = (args.workload, args.noise, ems[0].resolved_engine)
     out = {
@@ -317,7 +336,8 @@ def run_ours(args, rank, world, local_rank):
                      "kernel_ms_mean": round(kern_mean_ms, 5),
                      "kernel_ms_per_pack": round(kern_pack_ms, 5),
                      "kernel_ms_per_pack_min": round(kern_min_pack_ms, 5),
-                     "kernel_launches_timed": len(launch_ms), "packs_timed": KR * S},
+                     "kernel_launches_timed": len(launch_ms), "packs_timed": KR * S,
+                     "sequences_per_launch": S},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:

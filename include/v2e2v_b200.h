@@ -233,6 +233,16 @@ int v2e_pack_forward(const v2e_config* cfg, const v2e_pack* packs, int n_seq,
 int v2e_clip_forward(const v2e_config* cfg, const v2e_pack* packs, int n_packs,
                      void* workspace, size_t workspace_bytes, void* stream, void* const* events);
 
+/* -- a clip of a batch: consecutive steps of n_seq independent sequences in one call -------------
+ * packs[i * n_seq + s] is pack i of sequence s (s < n_seq <= V2E_MAX_SEQ_PER_LAUNCH); step i is
+ * one v2e_pack_forward(packs + i * n_seq, n_seq) launch, enqueued in order on `stream` with no
+ * host work in between (the reference runs the sequences of a batch one emulator after the other,
+ * one pack at a time: configs.py:62-63, test.py:115-121).  events: optional 2*n_packs
+ * cudaEvent_t, recorded before and after each step (NULL: none). */
+int v2e_batch_clip_forward(const v2e_config* cfg, const v2e_pack* packs, int n_packs, int n_seq,
+                           void* workspace, size_t workspace_bytes, void* stream,
+                           void* const* events);
+
 /* -- standalone event -> voxel grid (utils/event_process.py:15-63 / 66-129) ------------------
  * events: device f32 or f64 [n,4] rows (t,x,y,p), time-sorted.  Unlike the reference this does
  * NOT mutate `events`.  voxel: device f32 [num_bins,H,W], overwritten.  t_first/t_last are

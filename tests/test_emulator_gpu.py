@@ -335,6 +335,49 @@ def test_batch_of_sequences_equals_one_by_one(engine):
     assert batch.resolved_engine == ("fixpoint" if engine == "auto" else engine)
 
 
+@pytest.mark.parametrize("S,shared", [(3, True), (3, False), (18, True)])
+def test_batch_forward_clip_equals_step_loop(S, shared):
+    """EventEmulatorBatch.forward_clip (K steps, one C call per group of <= 16 sequences) == K
+    calls of EventEmulatorBatch.forward: voxel grids, counts and states bit-identical, with one
+    time base for the whole batch ([1, T] stamps, scalars shared) and with one row per sequence;
+    S = 18 spans two launch groups."""
+    from v2e2v_b200 import EventEmulatorBatch
+    cfg, T, K = gc.CFG2, 10, 5
+    H, W = (64, 96) if S > 16 else (260, 346)
+    planes = [gc.make_planes(70 + s, H, W, cfg) for s in range(S)]
+    vids = [list(gc.video(90 + s, K, T, H, W)) for s in range(S)]
+    frames = [torch.cat([vids[s][k][1] for s in range(S)]).cuda() for k in range(K)]
+    stamps = [vids[0][k][2] if shared else torch.cat([vids[s][k][2] for s in range(S)])
+              for k in range(K)]
+    res = []
+    for clip in (False, True):
+        batch = EventEmulatorBatch(S, device="cuda", noise_mode="philox", **cfg)
+        for s in range(S):
+            batch[s].philox_seed = 1000 + s
+            batch[s].set_planes(*planes[s])
+        if clip:
+            v1, n1 = batch.forward_clip(frames[:2], stamps[:2])
+            v2, n2 = batch.forward_clip(torch.stack(frames[2:]), stamps[2:])
+            vox, nev = torch.cat([v1, v2]), torch.cat([n1, n2])
+        else:
+            outs = [batch(frames[k], stamps[k].expand(S, -1) if shared else stamps[k])
+                    for k in range(K)]
+            vox, nev = torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
+        batch.check_status()
+        res.append((vox.cpu().numpy(), nev.cpu().numpy(),
+                    [batch[s].base_log_frame.cpu().numpy() for s in range(S)],
+                    [batch[s].timestamp_mem.cpu().numpy() for s in range(S)],
+                    [batch[s].t_previous for s in range(S)]))
+    a, b = res
+    assert a[0].shape == (K, S, cfg["num_bins"], H, W) and a[1].shape == (K, S)
+    assert a[1].sum() > 0 and a[4] == b[4]
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[0], b[0])
+    for s in range(S):
+        np.testing.assert_array_equal(a[2][s], b[2][s])
+        np.testing.assert_array_equal(a[3][s], b[3][s])
+
+
 @pytest.mark.parametrize("T,nb,vdt", [(14, 5, torch.float32), (10, 3, torch.float32),
                                       (7, 8, torch.float32), (10, 5, torch.bfloat16)])
 def test_fixpoint_other_pack_shapes(T, nb, vdt):

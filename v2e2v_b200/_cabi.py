@@ -154,6 +154,8 @@ SYMBOLS = {
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "v2e_clip_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Pack), C.c_int,
                                    C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "v2e_batch_clip_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Pack), C.c_int, C.c_int,
+                                         C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
     "v2e_events_to_voxel": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_double, C.c_double, C.c_int,
                                       C.c_void_p, C.c_void_p]),

@@ -214,4 +214,25 @@ int v2e_clip_forward(const v2e_config* c, const v2e_pack* packs, int n_packs, vo
     return V2E_OK;
 }
 
+int v2e_batch_clip_forward(const v2e_config* c, const v2e_pack* packs, int n_packs, int n_seq,
+                           void* workspace, size_t workspace_bytes, void* stream,
+                           void* const* events) {
+    if (!packs || n_packs < 1 || n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH) return V2E_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n_packs; ++i) {
+        if (events && events[2 * i]) {
+            const int rc = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i], st));
+            if (rc != V2E_OK) return rc;
+        }
+        const int rc = v2e_pack_forward(c, packs + (size_t)i * n_seq, n_seq, workspace, workspace_bytes,
+                                        stream);
+        if (rc != V2E_OK) return rc;
+        if (events && events[2 * i + 1]) {
+            const int rc2 = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i + 1], st));
+            if (rc2 != V2E_OK) return rc2;
+        }
+    }
+    return V2E_OK;
+}
+
 }  // extern "C"

@@ -339,6 +339,41 @@ class EventEmulator(nn.Module):
         pk.philox_seed = self.philox_seed
         pk.philox_offset = self._pack_counter
         self._pack_counter += 1
+        self._pk_last = pk
+
+    def _time_state_key(self):
+        """What the per-pack scalars depend on besides the stamps (host_scalars.pack_scalars)."""
+        return (self._t_prev.value, self._t_prev.is_f64, self.base_log_frame is None, self.num_bins,
+                self._refractory_host, self.cutoff_hz, self.ql, self.qs, self.shot_noise_rate_hz)
+
+    def _prep_pack_like(self, pk, fr, src, vox_ptr, meta_ptr):
+        """`_prep_pack` for a sequence that shares its time stamps with sequence `src` of the
+        batch (an emulator whose pack `src._pk_last` was just prepared from the same stamps and
+        the same time state): the scalars are copied instead of recomputed."""
+        num_frames, height, width = fr.shape
+        if self.base_log_frame is None:
+            ext = getattr(self, "_planes_external", False)
+            keep = (self.pos_thres, self.neg_thres, self.noise_rate_array) if ext else None
+            self._init(height, width)
+            if ext:
+                self.pos_thres, self.neg_thres, self.noise_rate_array = keep
+        C.memmove(C.byref(pk.sc), C.byref(src._pk_last.sc), C.sizeof(pk.sc))
+        self._t_prev.value, self._t_prev.is_f64 = src._t_prev.value, src._t_prev.is_f64
+        self.t_previous = self._t_prev.value
+        self.frame_counter += num_frames
+        pk.frames = fr.data_ptr()
+        pk.base_log_frame = self.base_log_frame.data_ptr()
+        pk.lp_log_frame0 = self.lp_log_frame0.data_ptr()
+        pk.timestamp_mem = self.timestamp_mem.data_ptr()
+        pk.pos_thres = self.pos_thres.data_ptr()
+        pk.neg_thres = self.neg_thres.data_ptr()
+        pk.noise_rate = ops._ptr(self.noise_rate_array)
+        pk.voxel = vox_ptr
+        pk.num_events = meta_ptr
+        pk.status = meta_ptr + 8
+        pk.philox_seed = self.philox_seed
+        pk.philox_offset = self._pack_counter
+        self._pack_counter += 1
 
     def forward_clip(self, frames, t_frames, events=None):
         """Emulate K consecutive packs in one call (extension; voxel_grid output only).
@@ -589,6 +624,18 @@ class EventEmulator(nn.Module):
         return out, n
 
 
+class _FrameView:
+    """[T, H, W] slice of a contiguous device tensor, by address (no torch indexing op on the
+    enqueue path)."""
+    __slots__ = ("_ptr", "shape")
+
+    def __init__(self, ptr, shape):
+        self._ptr, self.shape = ptr, shape
+
+    def data_ptr(self):
+        return self._ptr
+
+
 class EventEmulatorBatch(nn.Module):
     """S independent sequences emulated together (extension): one `EventEmulator` (batch size 1,
     the only well-defined batch semantics of the reference, SURVEY.md trap T1) per sequence, but
@@ -657,6 +704,100 @@ class EventEmulatorBatch(nn.Module):
         if self._meta is not None:
             meta, self._meta = self._meta, None
             EventEmulator._raise_on_status(int(meta[:, 2].max().item()))
+
+    def forward_clip(self, frames, t_frames, events=None):
+        """K consecutive steps of the batch in one call (extension): step k is what
+        ``forward(frames[k], t_frames[k])`` does - one launch per group of up to 16 sequences -
+        but the launches of a group are enqueued back to back by one C call
+        (`v2e_batch_clip_forward`) with every host-side scalar prepared ahead.
+
+        frames: [K, S, T, H, W] on the CUDA device, or a sequence of K tensors [S, T, H, W];
+        t_frames: a sequence of K stamp tensors, each [S, 2] / [S, T] (one row per sequence) or
+        [1, 2] / [1, T] (one time base for the whole batch: its scalars are computed once per
+        step and shared by the sequences that are in the same time state).
+        events: optional list of 2K torch.cuda.Event per GROUP of 16 sequences (a flat list of
+        2K * n_groups), recorded before / after each step's launch.
+        Returns (voxels [K, S, num_bins, H, W], num_events int64 [K, S] on the device); nothing
+        synchronises (call `check_status()`).
+        """
+        S = len(self.emulators)
+        frames = list(frames)
+        K = len(frames)
+        if K < 1 or len(t_frames) != K:
+            raise ValueError("need K >= 1 steps and one stamp tensor per step")
+        f0 = frames[0]
+        if f0.dim() != 4 or f0.size(0) != S:
+            raise ValueError("each step's frames must be [n_sequences, num_frames, height, width]")
+        if not f0.is_cuda:
+            raise RuntimeError("frames must be on the CUDA device (no CPU fallback)")
+        dtype = f0.dtype if f0.dtype in ops._FRAME_DT else torch.float32
+        T, H, W = f0.shape[1:]
+        if not (2 <= T <= _cabi.MAX_FRAMES):
+            raise ValueError(f"num_frames must be in [2,{_cabi.MAX_FRAMES}]")
+        em0 = self.emulators[0]
+        dev = em0._dev
+        out = torch.empty((K, S, em0.num_bins, H, W), dtype=em0.voxel_dtype, device=dev)
+        meta = torch.zeros((K, S, 4), dtype=torch.int32, device=dev)
+        ostride = out.stride(1) * out.element_size()
+        out_ptr, meta_ptr = out.data_ptr(), meta.data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        groups = self._get_groups(H, W, dtype)
+        lib = _cabi.lib()
+        packs = [(_cabi.Pack * (K * n))() for _, n, _, _ in groups]
+        evp = None
+        if events is not None:
+            if len(events) != 2 * K * len(groups):
+                raise ValueError("need 2 events per step and group")
+            evp = (C.c_void_p * len(events))()
+            for i, e in enumerate(events):
+                e.record()                      # forces creation of the cudaEvent_t
+                evp[i] = e.cuda_event
+        keep = []
+        # steps are prepared and enqueued in growing chunks (see EventEmulator.forward_clip)
+        k0, chunk, prev = 0, 1, 0
+        while k0 < K:
+            k1 = min(K, k0 + chunk)
+            for k in range(k0, k1):
+                fr = frames[k]
+                if fr.shape != f0.shape or not fr.is_cuda:
+                    raise ValueError("all steps share one frame shape and device")
+                if fr.dtype != dtype:
+                    fr = fr.to(dtype)
+                fr = fr.contiguous()
+                keep.append(fr)
+                tf = t_frames[k]
+                shared = tf.size(0) == 1 and S > 1
+                fstride = fr.stride(0) * fr.element_size()
+                fbase = fr.data_ptr()
+                for g, (a, n, pl, ws) in enumerate(groups):
+                    pk = packs[g]
+                    for j in range(n):
+                        i = a + j
+                        em = self.emulators[i]
+                        # (a [T, H, W] view of the step's frames without a torch indexing op)
+                        fr_i = _FrameView(fbase + i * fstride, (T, H, W))
+                        vox = out_ptr + (k * S + i) * ostride
+                        mp = meta_ptr + 16 * (k * S + i)
+                        if shared and i > 0 and em._time_state_key() == key0:
+                            em._prep_pack_like(pk[k * n + j], fr_i, self.emulators[0], vox, mp)
+                        else:
+                            if i == 0:
+                                key0 = em._time_state_key()   # (before the step)
+                            em._prep_pack(pk[k * n + j], fr_i, tf if shared else tf[i:i + 1], vox, mp)
+            for g, (a, n, pl, ws) in enumerate(groups):
+                pk0 = C.cast(C.addressof(packs[g]) + k0 * n * C.sizeof(_cabi.Pack), C.POINTER(_cabi.Pack))
+                ev0 = None
+                if evp is not None:
+                    ev0 = C.cast(C.addressof(evp) + (g * 2 * K + 2 * k0) * C.sizeof(C.c_void_p),
+                                 C.POINTER(C.c_void_p))
+                rc = lib.v2e_batch_clip_forward(C.byref(pl.cfg), pk0, k1 - k0, n, ws.data_ptr(),
+                                                ws.numel(), stream, ev0)
+                _cabi.check(rc, "v2e_batch_clip_forward")
+            k0, chunk, prev = k1, min(chunk + prev if prev else 1, 16), chunk
+        self._keep = (keep, packs)
+        self._meta = meta.reshape(K * S, 4)
+        num_events = meta[:, :, 0:2].contiguous().view(torch.int64).reshape(K, S)
+        return out, num_events
 
     def forward(self, frames, t_frames):
         S = len(self.emulators)
