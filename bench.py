@@ -68,15 +68,55 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed regions run: NVML in-process (the
+    rank's own GPU, every 10 ms - spawning nvidia-smi from every rank every 50 ms stalled other
+    ranks' launches in the multi-GPU runs), nvidia-smi as the fall-back."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self.source = None
+        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "10")) * 1e-3
+
+    def _nvml_loop(self) -> bool:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML wants the physical device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                tok = vis.split(",")[self.index].strip()
+                h = nv.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else \
+                    nv.nvmlDeviceGetHandleByIndex(int(tok))
+            else:
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [(nv.nvmlClocksEventReasonHwSlowdown, 0), (nv.nvmlClocksEventReasonHwThermalSlowdown, 1),
+                    (nv.nvmlClocksEventReasonSwThermalSlowdown, 2), (nv.nvmlClocksEventReasonSwPowerCap, 3)]
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            return False
+        self.source = "nvml"
+        while not self._halt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+        return True
 
     def run(self):
         if os.environ.get("BENCH_NO_SAMPLER"):     # development aid
             return
+        if not os.environ.get("BENCH_SAMPLER_SMI") and self._nvml_loop():
+            return
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -96,10 +136,9 @@ class ClockSampler(threading.Thread):
         self.join(timeout=6)
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         mx = max([int(r[1]) for r in self.rows if r[1].isdigit()] or [0])
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:]) if v == "Active"})
+        reasons = sorted({n for r in self.rows for n, v in zip(self.NAMES, r[2:]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 def synth_pack_device(gen, base, H, W, dtype=torch.float32):
@@ -208,15 +247,19 @@ def run_ours(args, rank, world, local_rank):
     for kk in range(0, Wm + CL + K + min(K, 200) + 8):
         stamps(kk)
     # warm the clip path too (its output block comes from cudaMalloc the first time: ~40 ms)
+    import gc
+    gc.collect()        # (before the warm clip: the device must not sit idle ahead of the timed region)
     k = run_clips(k, CL)
     clip_ev.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.disable()        # no collector pause between two enqueues of the timed region
     barrier()
     launches0 = lib.v2e_launch_count()
     e0.record()
     k = run_clips(k, K)
     e1.record()
     barrier()
+    gc.enable()
     if batch is not None:
         batch.check_status()
     else:

@@ -205,6 +205,25 @@ typedef struct v2e_host_params {
 int v2e_host_pack_scalars(const v2e_host_params* hp, const double* t_frames,
                           const float* time_frames, v2e_pack_scalars* out);
 
+/* K consecutive packs of ONE sequence prepared by one host call (pure host code): the scalars
+ * of each pack as v2e_host_pack_scalars gives them with t_previous carried from pack to pack
+ * (v2e_model.py:521; hp0->first_pack / t_prev / t_prev_f64 describe the state before pack 0),
+ * plus the per-pack pointers.  The caller's loop `for pack in clip` (test.py:115-121) costs tens
+ * of microseconds of interpreter time per pack, as much as a third of a kernel; this is the same
+ * work in well under a microsecond.  Serves the usual stamp layout only: every row holds
+ * hp0->n_stamps >= num_frames float64 stamps (stamps_f64 / t_range_f64 / t_start / t_end of hp0
+ * are ignored and derived per row).
+ *   out[i] = *tmpl with frames = frames[i], voxel = tmpl->voxel + i * voxel_stride_bytes,
+ *   num_events / status = tmpl's + 16 bytes * i (one 16-byte record per pack),
+ *   philox_offset = tmpl->philox_offset + i, sc = the pack's scalars.
+ * On V2E_ERR_TIME_ORDER (or any other error) *failed_at is the pack index, nothing else is
+ * reported and *t_prev_out is not written.  On success *t_prev_out = the last pack's last stamp
+ * (a float64 t_previous). */
+int v2e_host_clip_prepare(const v2e_host_params* hp0, const double* const* stamp_rows,
+                          const float* time_frames, const v2e_pack* tmpl, const void* const* frames,
+                          size_t voxel_stride_bytes, int n_packs, double* t_prev_out,
+                          int32_t* failed_at, v2e_pack* out);
+
 /* -- the hot path ----------------------------------------------------------------------------
  * Emulate one pack for each of n_seq independent sequences (1 <= n_seq <= 16 per call).
  * Replaces EventEmulator.forward (v2e/v2e_model.py:290-536) for B=1 per sequence.  State planes

@@ -13,6 +13,7 @@
  * tests/test_host_scalars.py checks bit-equality with the torch expressions.
  */
 #include <math.h>
+#include <stddef.h>
 #include <string.h>
 
 #include "../../include/v2e2v_b200.h"
@@ -101,5 +102,45 @@ int v2e_host_pack_scalars(const v2e_host_params* hp, const double* t_frames,
         tprev_f64 = hp->stamps_f64;
     }
     out->shot_f64_mask = mask;
+    return V2E_OK;
+}
+
+/* K consecutive packs of one sequence prepared by one host call: what the caller's pack loop
+ * (test.py:115-121) does K times around v2e_host_pack_scalars - t_previous carried from pack to
+ * pack (v2e_model.py:521), first_pack only for the first - plus the per-pack pointers. */
+int v2e_host_clip_prepare(const v2e_host_params* hp0, const double* const* stamp_rows,
+                          const float* time_frames, const v2e_pack* tmpl, const void* const* frames,
+                          size_t voxel_stride_bytes, int n_packs, double* t_prev_out,
+                          int32_t* failed_at, v2e_pack* out) {
+    if (!hp0 || !stamp_rows || !time_frames || !tmpl || !frames || !out || n_packs < 1)
+        return V2E_ERR_BAD_ARG;
+    v2e_host_params hp = *hp0;
+    hp.stamps_f64 = 1;
+    hp.t_range_f64 = 1;
+    const int T = hp.num_frames;
+    if (T < 2 || T > V2E_MAX_FRAMES || hp.n_stamps < T) return V2E_ERR_BAD_ARG;
+    for (int i = 0; i < n_packs; ++i) {
+        const double* row = stamp_rows[i];
+        if (!row || !frames[i]) return V2E_ERR_BAD_ARG;
+        hp.t_start = row[0];
+        hp.t_end = row[hp.n_stamps - 1];
+        v2e_pack* p = &out[i];
+        /* (everything but the scalars, which the call below fills) */
+        memcpy(p, tmpl, offsetof(v2e_pack, sc));
+        p->frames = frames[i];
+        p->voxel = (char*)tmpl->voxel + (size_t)i * voxel_stride_bytes;
+        p->num_events = (int64_t*)((char*)tmpl->num_events + (size_t)i * 16);
+        p->status = tmpl->status ? (int32_t*)((char*)tmpl->status + (size_t)i * 16) : 0;
+        p->philox_offset = tmpl->philox_offset + (uint64_t)i;
+        const int rc = v2e_host_pack_scalars(&hp, row, time_frames, &p->sc);
+        if (rc != V2E_OK) {
+            if (failed_at) *failed_at = i;
+            return rc;
+        }
+        hp.first_pack = 0;
+        hp.t_prev = row[T - 1];
+        hp.t_prev_f64 = 1;
+    }
+    if (t_prev_out) *t_prev_out = hp.t_prev;
     return V2E_OK;
 }

@@ -165,6 +165,8 @@ class EventEmulator(nn.Module):
         self.debug_maps = debug_maps
         self.debug_shot_imax = debug_shot_imax
         self.lazy_num_events = lazy_num_events
+        self._clip_trace = None   # development aid: list that receives (label, perf_counter) marks
+        self.clip_ramp = None   # development aid: packs per enqueue chunk of forward_clip (None: Fibonacci ramp)
         # None: uint8 frames are integer by construction, float frames are not assumed to be.
         # True: the caller guarantees integer-valued frames in 0..255 (what every reader of the
         # reference produces); a violation is detected on the device and raised as ValueError.
@@ -177,6 +179,8 @@ class EventEmulator(nn.Module):
         self.inject_shot_rand = None
         self.philox_seed = (int(torch.initial_seed()) ^ 0x5851F42D4C957F2D) & (2 ** 64 - 1)
         self._pack_counter = 0
+        self._first_pending = False
+        self._clip_tmpl = _cabi.Pack()
         self._t_prev = TimeState()
         self._launch = None
         self._launch_key = None
@@ -234,6 +238,7 @@ class EventEmulator(nn.Module):
         self.base_log_frame = None
         self.lp_log_frame0 = None
         self.frame_counter = 0
+        self._first_pending = False
 
     # ------------------------------------------------------------------------------------------
     def _config(self, H, W, frame_dtype) -> _cabi.Config:
@@ -307,10 +312,9 @@ class EventEmulator(nn.Module):
                 _cabi.ENGINE_RUNAHEAD: "runahead",
                 _cabi.ENGINE_FIXPOINT: "fixpoint"}.get(self._launch.resolve_engine())
 
-    def _prep_pack(self, pk, fr, t_frames, vox_ptr, meta_ptr):
-        """Fill one v2e_pack (voxel output, no debug maps) for frames `fr` [T,H,W] and advance the
-        host-side state (time, pack counter).  meta_ptr: 16 zeroed bytes (num_events i64, status)."""
-        num_frames, height, width = fr.shape
+    def _first_pack_init(self, height, width) -> bool:
+        """True (after creating the per-sequence state, v2e_model.py:325-327) when the next pack
+        is the first one after reset()."""
         first = self.base_log_frame is None
         if first:
             ext = getattr(self, "_planes_external", False)
@@ -318,11 +322,63 @@ class EventEmulator(nn.Module):
             self._init(height, width)
             if ext:
                 self.pos_thres, self.neg_thres, self.noise_rate_array = keep
+        elif self._first_pending:
+            # (a refused chunk preparation had already created the state)
+            first, self._first_pending = True, False
+        return first
+
+    def _get_scalar_prep(self, num_frames) -> PackScalarPrep:
         key = (num_frames, self.num_bins, float(self._refractory_host), float(self.cutoff_hz),
                float(self.ql), float(self.qs), float(self.shot_noise_rate_hz))
         prep = getattr(self, "_scalar_prep", None)
         if prep is None or prep.key != key:
             prep = self._scalar_prep = PackScalarPrep(*key)
+        return prep
+
+    def _prep_chunk_c(self, pk0, n, fptrs, rows, n_stamps, num_frames, height, width,
+                      vox_ptr, vox_stride, meta_ptr) -> bool:
+        """`_prep_pack` for n consecutive packs in ONE C call (`v2e_host_clip_prepare`): frames by
+        device address, stamps as host float64 rows of n_stamps >= num_frames entries.  False
+        (nothing changed) when the C routine refuses - the caller then takes the per-pack path,
+        which raises what has to be raised."""
+        first = self._first_pack_init(height, width)
+        prep = self._get_scalar_prep(num_frames)
+        hp = prep.hp
+        hp.n_stamps = n_stamps
+        hp.first_pack = int(first)
+        hp.t_prev = self._t_prev.value
+        hp.t_prev_f64 = int(self._t_prev.is_f64)
+        t = self._clip_tmpl
+        t.base_log_frame = self.base_log_frame.data_ptr()
+        t.lp_log_frame0 = self.lp_log_frame0.data_ptr()
+        t.timestamp_mem = self.timestamp_mem.data_ptr()
+        t.pos_thres = self.pos_thres.data_ptr()
+        t.neg_thres = self.neg_thres.data_ptr()
+        t.noise_rate = ops._ptr(self.noise_rate_array)
+        t.voxel = vox_ptr
+        t.num_events = meta_ptr
+        t.status = meta_ptr + 8
+        t.philox_seed = self.philox_seed
+        t.philox_offset = self._pack_counter
+        tp, bad = C.c_double(0.0), C.c_int32(-1)
+        rc = _cabi.lib().v2e_host_clip_prepare(prep._hp_ref, rows, prep._tfr_ptr, C.byref(t), fptrs,
+                                               vox_stride, n, C.byref(tp), C.byref(bad), pk0)
+        if rc != _cabi.OK:
+            if first:   # (the per-pack path must see a first pack again)
+                self._first_pending = True
+            return False
+        self._t_prev.value, self._t_prev.is_f64 = tp.value, True
+        self.t_previous = tp.value
+        self.frame_counter += n * num_frames
+        self._pack_counter += n
+        return True
+
+    def _prep_pack(self, pk, fr, t_frames, vox_ptr, meta_ptr):
+        """Fill one v2e_pack (voxel output, no debug maps) for frames `fr` [T,H,W] and advance the
+        host-side state (time, pack counter).  meta_ptr: 16 zeroed bytes (num_events i64, status)."""
+        num_frames, height, width = fr.shape
+        first = self._first_pack_init(height, width)
+        prep = self._get_scalar_prep(num_frames)
         prep.fill(t_frames, self._t_prev, first, pk.sc)
         self.t_previous = self._t_prev.value
         self.frame_counter += num_frames
@@ -420,10 +476,15 @@ class EventEmulator(nn.Module):
         if not (2 <= num_frames <= _cabi.MAX_FRAMES):
             raise ValueError(f"num_frames must be in [2,{_cabi.MAX_FRAMES}]")
         dev = self._dev
+        tr = self._clip_trace
+        if tr is not None:
+            import time as _t
+            tr.append(("entry+norm", _t.perf_counter()))
         pl = self._get_launch(height, width, frames[0].dtype)
         packs = (_cabi.Pack * K)()
         out = torch.empty((K, self.num_bins, height, width), dtype=self.voxel_dtype, device=dev)
-        meta = torch.zeros((K, 4), dtype=torch.int32, device=dev)   # num_events (i64), status, pad
+        # one 16-byte record per pack: num_events (i64), status (i32), pad
+        meta = torch.zeros((K, 2), dtype=torch.int64, device=dev)
         ostride = out.stride(0) * out.element_size()
         evp = None
         if events is not None:
@@ -433,33 +494,79 @@ class EventEmulator(nn.Module):
             for i, e in enumerate(events):
                 e.record()                      # forces creation of the cudaEvent_t
                 evp[i] = e.cuda_event
-        # The host-side preparation of a pack (stamps -> scalars, the torch expressions of
-        # v2e_model.py:303-318) costs about half a kernel: packs are prepared and enqueued in
-        # growing chunks, so that the device works on chunk i while the host prepares chunk i+1.
+        # Packs are prepared and enqueued in growing chunks, so that the device works on chunk i
+        # while the host prepares chunk i+1.  A chunk whose stamps are host float64 rows (what the
+        # reference's readers produce) and whose frames are contiguous is prepared by ONE C call
+        # (`v2e_host_clip_prepare`, well under a microsecond per pack); anything else goes pack
+        # by pack through `_prep_pack` (the torch expressions of v2e_model.py:303-318, ~10 us).
+        if tr is not None:
+            tr.append(("alloc+events", _t.perf_counter()))
         stream = torch.cuda.current_stream(dev).cuda_stream
         out_ptr, meta_ptr = out.data_ptr(), meta.data_ptr()
-        k0, chunk, prev = 0, 1, 0     # chunks of 1, 1, 2, 3, 5, 8, 13, 16, 16, ... packs: the host
-        while k0 < K:                 # prepares a pack in about half the time the device needs for it
+        dt0, shp0 = frames[0].dtype, frames[0].shape
+        f64 = torch.float64
+        sizeof_pack, sizeof_vp = C.sizeof(_cabi.Pack), C.sizeof(C.c_void_p)
+        # chunks: one pack first (the device starts after ~70 us of host time), then as many as a
+        # launch chains when the C preparation serves the clip; 1, 1, 2, 3, 5, 8, 13, 16, ... packs
+        # when the packs are prepared one by one (the host then needs about a fifth of the
+        # device's time per pack)
+        k0, chunk, prev = 0, 1, 0
+        ramp = self.clip_ramp
+        if ramp is None:
+            tf0 = t_frames[0]
+            if (tf0.dim() == 2 and tf0.dtype == f64 and not tf0.is_cuda and tf0.shape[1] != 2
+                    and tf0.shape[1] >= num_frames):
+                ramp = (1, _cabi.MAX_SEQ_PER_LAUNCH)
+        ci = 0
+        while k0 < K:
+            if ramp is not None:
+                chunk = ramp[min(ci, len(ramp) - 1)]
+                ci += 1
             k1 = min(K, k0 + chunk)
-            for k in range(k0, k1):
-                if k:
-                    frames[k] = norm(frames[k])
-                    if frames[k].shape != frames[0].shape or frames[k].dtype != frames[0].dtype:
-                        raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
-                self._prep_pack(packs[k], frames[k], t_frames[k], out_ptr + k * ostride,
-                                meta_ptr + 16 * k)
-            pk0 = C.cast(C.addressof(packs) + k0 * C.sizeof(_cabi.Pack), C.POINTER(_cabi.Pack))
+            n = k1 - k0
+            pk0 = C.cast(C.addressof(packs) + k0 * sizeof_pack, C.POINTER(_cabi.Pack))
+            # ---- the chunk in one C call, when its inputs have the usual layout
+            fptrs, rows, n_st = [], [], t_frames[k0].shape[-1] if t_frames[k0].dim() == 2 else 0
+            fast = n_st >= num_frames and n_st != 2
+            if fast:
+                for k in range(k0, k1):
+                    fr, tf = frames[k], t_frames[k]
+                    if not (fr.is_cuda and fr.dtype == dt0 and fr.shape[-3:] == shp0
+                            and fr.is_contiguous() and tf.dtype == f64 and tf.dim() == 2
+                            and tf.shape[1] == n_st and tf.shape[0] >= 1 and not tf.is_cuda
+                            and tf.is_contiguous() and not tf.requires_grad):
+                        fast = False
+                        break
+                    fptrs.append(fr.data_ptr())
+                    rows.append(tf.data_ptr())
+            if fast:
+                fast = self._prep_chunk_c(pk0, n, (C.c_void_p * n)(*fptrs), (C.c_void_p * n)(*rows),
+                                          n_st, num_frames, height, width,
+                                          out_ptr + k0 * ostride, ostride, meta_ptr + 16 * k0)
+            if not fast:
+                for k in range(k0, k1):
+                    if k:
+                        frames[k] = norm(frames[k])
+                        if frames[k].shape != shp0 or frames[k].dtype != dt0:
+                            raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
+                    self._prep_pack(packs[k], frames[k], t_frames[k], out_ptr + k * ostride,
+                                    meta_ptr + 16 * k)
             ev0 = None
             if evp is not None:
-                ev0 = C.cast(C.addressof(evp) + 2 * k0 * C.sizeof(C.c_void_p), C.POINTER(C.c_void_p))
-            rc = pl._lib.v2e_clip_forward(C.byref(pl.cfg), pk0, k1 - k0, self._workspace.data_ptr(),
+                ev0 = C.cast(C.addressof(evp) + 2 * k0 * sizeof_vp, C.POINTER(C.c_void_p))
+            if tr is not None:
+                tr.append((f"prep {n}", _t.perf_counter()))
+            rc = pl._lib.v2e_clip_forward(C.byref(pl.cfg), pk0, n, self._workspace.data_ptr(),
                                           self._workspace.numel(), stream, ev0)
             _cabi.check(rc, "v2e_clip_forward")
+            if tr is not None:
+                tr.append((f"enqueue {n}", _t.perf_counter()))
             k0, chunk, prev = k1, min(chunk + prev if prev else 1, 16), chunk
         self._clip_keep = (frames, packs)       # keep the inputs alive until the stream is done
-        self._last_meta = meta[-1]
-        self._clip_meta = meta
-        num_events = meta[:, 0:2].contiguous().view(torch.int64).reshape(K)
+        meta32 = meta.view(torch.int32)         # [K, 4]: num_events lo/hi, status, pad
+        self._last_meta = meta32[-1]
+        self._clip_meta = meta32
+        num_events = meta[:, 0]
         self.num_events = num_events
         return out, num_events
 
