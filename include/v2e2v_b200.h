@@ -212,17 +212,23 @@ int v2e_host_pack_scalars(const v2e_host_params* hp, const double* t_frames,
  * of microseconds of interpreter time per pack, as much as a third of a kernel; this is the same
  * work in well under a microsecond.  Serves the usual stamp layout only: every row holds
  * hp0->n_stamps >= num_frames float64 stamps (stamps_f64 / t_range_f64 / t_start / t_end of hp0
- * are ignored and derived per row).
- *   out[i] = *tmpl with frames = frames[i], voxel = tmpl->voxel + i * voxel_stride_bytes,
- *   num_events / status = tmpl's + 16 bytes * i (one 16-byte record per pack),
- *   philox_offset = tmpl->philox_offset + i, sc = the pack's scalars.
+ * are ignored and derived per row).  For pack i:
+ *   row        = (double*)((char*)stamp_rows[i] + row_offset_bytes)
+ *   o          = out[i * out_stride]   (out_stride > 1: the sequence is one of a batch whose
+ *                                       step records are interleaved, v2e_batch_clip_forward)
+ *   o          = *tmpl, then
+ *   o.frames   = (char*)frames[i] + frame_offset_bytes
+ *   o.voxel    = tmpl->voxel + i * voxel_stride_bytes
+ *   o.num_events / o.status = tmpl's + i * meta_stride_bytes
+ *   o.philox_offset = tmpl->philox_offset + i,   o.sc = the pack's scalars.
  * On V2E_ERR_TIME_ORDER (or any other error) *failed_at is the pack index, nothing else is
  * reported and *t_prev_out is not written.  On success *t_prev_out = the last pack's last stamp
  * (a float64 t_previous). */
 int v2e_host_clip_prepare(const v2e_host_params* hp0, const double* const* stamp_rows,
-                          const float* time_frames, const v2e_pack* tmpl, const void* const* frames,
-                          size_t voxel_stride_bytes, int n_packs, double* t_prev_out,
-                          int32_t* failed_at, v2e_pack* out);
+                          size_t row_offset_bytes, const float* time_frames, const v2e_pack* tmpl,
+                          const void* const* frames, size_t frame_offset_bytes,
+                          size_t voxel_stride_bytes, size_t meta_stride_bytes, int n_packs,
+                          int out_stride, double* t_prev_out, int32_t* failed_at, v2e_pack* out);
 
 /* -- the hot path ----------------------------------------------------------------------------
  * Emulate one pack for each of n_seq independent sequences (1 <= n_seq <= 16 per call).

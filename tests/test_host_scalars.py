@@ -106,3 +106,61 @@ def test_ts_step_formula():
             want = float((duration / torch.tensor([ni], dtype=torch.int32))[0])
             got = np.float32(np.float32(1.0) / np.float32(ni)) * np.float32(duration)
             assert np.float32(want) == got
+
+
+@pytest.mark.parametrize("first", [True, False])
+def test_clip_prepare_equals_pack_loop(first):
+    """v2e_host_clip_prepare (K packs of a sequence in one host call) == K calls of
+    v2e_host_pack_scalars with t_previous carried along, plus the per-pack pointers."""
+    import ctypes as C
+    from v2e2v_b200 import _cabi
+    from v2e2v_b200.host_scalars import PackScalarPrep
+    T, nb, K, n_st = 10, 5, 7, 11
+    prep = PackScalarPrep(T, nb, 0.001, 200.0, 1.0, 0.0, 1.0)
+    rows = [torch.linspace(k * 0.009 + 0.5, (k + 1) * 0.009 + 0.5, n_st, dtype=torch.float64)[None]
+            for k in range(K)]
+    tp = TimeState(0.25, False)
+    want = []
+    tp_loop = TimeState(tp.value, tp.is_f64)
+    for k in range(K):
+        sc = _cabi.PackScalars()
+        prep.fill(rows[k], tp_loop, first and k == 0, sc)
+        want.append(bytes(sc))
+    tmpl = _cabi.Pack()
+    tmpl.base_log_frame, tmpl.voxel, tmpl.num_events, tmpl.status = 0x1000, 0x200000, 0x3000, 0x3008
+    tmpl.philox_seed, tmpl.philox_offset = 77, 5
+    hp = prep.hp
+    hp.n_stamps, hp.first_pack, hp.t_prev, hp.t_prev_f64 = n_st, int(first), tp.value, int(tp.is_f64)
+    out = (_cabi.Pack * K)()
+    fptrs = (C.c_void_p * K)(*[0x900000 + 64 * k for k in range(K)])
+    rptrs = (C.c_void_p * K)(*[r.data_ptr() for r in rows])
+    tprev, bad = C.c_double(0), C.c_int32(-1)
+    rc = _cabi.lib().v2e_host_clip_prepare(C.byref(hp), rptrs, 0, prep._tfr_ptr, C.byref(tmpl), fptrs, 0,
+                                           4096, 16, K, 1, C.byref(tprev), C.byref(bad), out)
+    assert rc == _cabi.OK and tprev.value == tp_loop.value
+    for k in range(K):
+        assert bytes(out[k].sc) == want[k], f"pack {k}"
+        assert out[k].frames == 0x900000 + 64 * k and out[k].voxel == 0x200000 + 4096 * k
+        assert out[k].num_events == 0x3000 + 16 * k and out[k].status == 0x3008 + 16 * k
+        assert out[k].philox_offset == 5 + k and out[k].philox_seed == 77
+        assert out[k].base_log_frame == 0x1000
+    # one sequence of a batch: records interleaved (out_stride), frames / rows / meta by offset
+    out2 = (_cabi.Pack * (3 * K))()
+    big = torch.stack([torch.cat([r, r + 100.0]) for r in rows])      # [K, 2, n_st]: row 1 = +100 s
+    rp2 = (C.c_void_p * K)(*[big[k].data_ptr() for k in range(K)])
+    hp.t_prev = 50.0
+    rc = _cabi.lib().v2e_host_clip_prepare(C.byref(hp), rp2, n_st * 8, prep._tfr_ptr, C.byref(tmpl), fptrs, 32,
+                                           4096, 48, K, 3, C.byref(tprev), C.byref(bad),
+                                           C.cast(C.addressof(out2) + C.sizeof(_cabi.Pack), C.POINTER(_cabi.Pack)))
+    assert rc == _cabi.OK and tprev.value == float(big[K - 1, 1, T - 1])
+    for k in range(K):
+        o = out2[3 * k + 1]
+        assert o.frames == 0x900000 + 64 * k + 32 and o.num_events == 0x3000 + 48 * k
+        assert o.sc.num_frames == T and out2[3 * k].sc.num_frames == 0
+    hp.t_prev = tp.value
+    # a clip that goes back in time is refused at the offending pack, nothing is reported done
+    rptrs[3] = rows[1].data_ptr()
+    tprev.value = -1.0
+    rc = _cabi.lib().v2e_host_clip_prepare(C.byref(hp), rptrs, 0, prep._tfr_ptr, C.byref(tmpl), fptrs, 0,
+                                           4096, 16, K, 1, C.byref(tprev), C.byref(bad), out)
+    assert rc == _cabi.ERR_TIME_ORDER and bad.value == 3 and tprev.value == -1.0

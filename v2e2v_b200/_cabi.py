@@ -150,10 +150,10 @@ SYMBOLS = {
     "v2e_launch_count": (C.c_int64, []),
     "v2e_host_pack_scalars": (C.c_int, [C.POINTER(HostParams), C.POINTER(C.c_double),
                                         C.POINTER(C.c_float), C.POINTER(PackScalars)]),
-    "v2e_host_clip_prepare": (C.c_int, [C.POINTER(HostParams), C.POINTER(C.c_void_p),
+    "v2e_host_clip_prepare": (C.c_int, [C.POINTER(HostParams), C.POINTER(C.c_void_p), C.c_size_t,
                                         C.POINTER(C.c_float), C.POINTER(Pack), C.POINTER(C.c_void_p),
-                                        C.c_size_t, C.c_int, C.POINTER(C.c_double),
-                                        C.POINTER(C.c_int32), C.POINTER(Pack)]),
+                                        C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(Pack)]),
     "v2e_pack_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Pack), C.c_int,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     "v2e_clip_forward": (C.c_int, [C.POINTER(Config), C.POINTER(Pack), C.c_int,

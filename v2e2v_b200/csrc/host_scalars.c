@@ -109,10 +109,12 @@ int v2e_host_pack_scalars(const v2e_host_params* hp, const double* t_frames,
  * (test.py:115-121) does K times around v2e_host_pack_scalars - t_previous carried from pack to
  * pack (v2e_model.py:521), first_pack only for the first - plus the per-pack pointers. */
 int v2e_host_clip_prepare(const v2e_host_params* hp0, const double* const* stamp_rows,
-                          const float* time_frames, const v2e_pack* tmpl, const void* const* frames,
-                          size_t voxel_stride_bytes, int n_packs, double* t_prev_out,
-                          int32_t* failed_at, v2e_pack* out) {
-    if (!hp0 || !stamp_rows || !time_frames || !tmpl || !frames || !out || n_packs < 1)
+                          size_t row_offset_bytes, const float* time_frames, const v2e_pack* tmpl,
+                          const void* const* frames, size_t frame_offset_bytes,
+                          size_t voxel_stride_bytes, size_t meta_stride_bytes, int n_packs,
+                          int out_stride, double* t_prev_out, int32_t* failed_at, v2e_pack* out) {
+    if (!hp0 || !stamp_rows || !time_frames || !tmpl || !frames || !out || n_packs < 1 ||
+        out_stride < 1)
         return V2E_ERR_BAD_ARG;
     v2e_host_params hp = *hp0;
     hp.stamps_f64 = 1;
@@ -120,17 +122,17 @@ int v2e_host_clip_prepare(const v2e_host_params* hp0, const double* const* stamp
     const int T = hp.num_frames;
     if (T < 2 || T > V2E_MAX_FRAMES || hp.n_stamps < T) return V2E_ERR_BAD_ARG;
     for (int i = 0; i < n_packs; ++i) {
-        const double* row = stamp_rows[i];
-        if (!row || !frames[i]) return V2E_ERR_BAD_ARG;
+        if (!stamp_rows[i] || !frames[i]) return V2E_ERR_BAD_ARG;
+        const double* row = (const double*)((const char*)stamp_rows[i] + row_offset_bytes);
         hp.t_start = row[0];
         hp.t_end = row[hp.n_stamps - 1];
-        v2e_pack* p = &out[i];
+        v2e_pack* p = &out[(size_t)i * out_stride];
         /* (everything but the scalars, which the call below fills) */
         memcpy(p, tmpl, offsetof(v2e_pack, sc));
-        p->frames = frames[i];
+        p->frames = (const char*)frames[i] + frame_offset_bytes;
         p->voxel = (char*)tmpl->voxel + (size_t)i * voxel_stride_bytes;
-        p->num_events = (int64_t*)((char*)tmpl->num_events + (size_t)i * 16);
-        p->status = tmpl->status ? (int32_t*)((char*)tmpl->status + (size_t)i * 16) : 0;
+        p->num_events = (int64_t*)((char*)tmpl->num_events + (size_t)i * meta_stride_bytes);
+        p->status = tmpl->status ? (int32_t*)((char*)tmpl->status + (size_t)i * meta_stride_bytes) : 0;
         p->philox_offset = tmpl->philox_offset + (uint64_t)i;
         const int rc = v2e_host_pack_scalars(&hp, row, time_frames, &p->sc);
         if (rc != V2E_OK) {

@@ -336,7 +336,8 @@ class EventEmulator(nn.Module):
         return prep
 
     def _prep_chunk_c(self, pk0, n, fptrs, rows, n_stamps, num_frames, height, width,
-                      vox_ptr, vox_stride, meta_ptr) -> bool:
+                      vox_ptr, vox_stride, meta_ptr, meta_stride=16, frame_offset=0, row_offset=0,
+                      out_stride=1) -> bool:
         """`_prep_pack` for n consecutive packs in ONE C call (`v2e_host_clip_prepare`): frames by
         device address, stamps as host float64 rows of n_stamps >= num_frames entries.  False
         (nothing changed) when the C routine refuses - the caller then takes the per-pack path,
@@ -361,8 +362,9 @@ class EventEmulator(nn.Module):
         t.philox_seed = self.philox_seed
         t.philox_offset = self._pack_counter
         tp, bad = C.c_double(0.0), C.c_int32(-1)
-        rc = _cabi.lib().v2e_host_clip_prepare(prep._hp_ref, rows, prep._tfr_ptr, C.byref(t), fptrs,
-                                               vox_stride, n, C.byref(tp), C.byref(bad), pk0)
+        rc = _cabi.lib().v2e_host_clip_prepare(prep._hp_ref, rows, row_offset, prep._tfr_ptr, C.byref(t),
+                                               fptrs, frame_offset, vox_stride, meta_stride, n,
+                                               out_stride, C.byref(tp), C.byref(bad), pk0)
         if rc != _cabi.OK:
             if first:   # (the per-pack path must see a first pack again)
                 self._first_pending = True
@@ -380,41 +382,6 @@ class EventEmulator(nn.Module):
         first = self._first_pack_init(height, width)
         prep = self._get_scalar_prep(num_frames)
         prep.fill(t_frames, self._t_prev, first, pk.sc)
-        self.t_previous = self._t_prev.value
-        self.frame_counter += num_frames
-        pk.frames = fr.data_ptr()
-        pk.base_log_frame = self.base_log_frame.data_ptr()
-        pk.lp_log_frame0 = self.lp_log_frame0.data_ptr()
-        pk.timestamp_mem = self.timestamp_mem.data_ptr()
-        pk.pos_thres = self.pos_thres.data_ptr()
-        pk.neg_thres = self.neg_thres.data_ptr()
-        pk.noise_rate = ops._ptr(self.noise_rate_array)
-        pk.voxel = vox_ptr
-        pk.num_events = meta_ptr
-        pk.status = meta_ptr + 8
-        pk.philox_seed = self.philox_seed
-        pk.philox_offset = self._pack_counter
-        self._pack_counter += 1
-        self._pk_last = pk
-
-    def _time_state_key(self):
-        """What the per-pack scalars depend on besides the stamps (host_scalars.pack_scalars)."""
-        return (self._t_prev.value, self._t_prev.is_f64, self.base_log_frame is None, self.num_bins,
-                self._refractory_host, self.cutoff_hz, self.ql, self.qs, self.shot_noise_rate_hz)
-
-    def _prep_pack_like(self, pk, fr, src, vox_ptr, meta_ptr):
-        """`_prep_pack` for a sequence that shares its time stamps with sequence `src` of the
-        batch (an emulator whose pack `src._pk_last` was just prepared from the same stamps and
-        the same time state): the scalars are copied instead of recomputed."""
-        num_frames, height, width = fr.shape
-        if self.base_log_frame is None:
-            ext = getattr(self, "_planes_external", False)
-            keep = (self.pos_thres, self.neg_thres, self.noise_rate_array) if ext else None
-            self._init(height, width)
-            if ext:
-                self.pos_thres, self.neg_thres, self.noise_rate_array = keep
-        C.memmove(C.byref(pk.sc), C.byref(src._pk_last.sc), C.sizeof(pk.sc))
-        self._t_prev.value, self._t_prev.is_f64 = src._t_prev.value, src._t_prev.is_f64
         self.t_previous = self._t_prev.value
         self.frame_counter += num_frames
         pk.frames = fr.data_ptr()
@@ -860,10 +827,24 @@ class EventEmulatorBatch(nn.Module):
                 e.record()                      # forces creation of the cudaEvent_t
                 evp[i] = e.cuda_event
         keep = []
-        # steps are prepared and enqueued in growing chunks (see EventEmulator.forward_clip)
-        k0, chunk, prev = 0, 1, 0
+        # Steps are prepared and enqueued in chunks (see EventEmulator.forward_clip).  When the
+        # stamps are host float64 rows and the frames contiguous, a sequence's share of a chunk
+        # is prepared by one C call (`v2e_host_clip_prepare`, records interleaved by sequence).
+        f64 = torch.float64
+        sizeof_pack = C.sizeof(_cabi.Pack)
+        tf0 = t_frames[0]
+        n_st = tf0.shape[1] if tf0.dim() == 2 else 0
+        fast_clip = (n_st >= T and n_st != 2 and tf0.dtype == f64 and not tf0.is_cuda)
+        ramp = (1, _cabi.MAX_SEQ_PER_LAUNCH) if fast_clip else None
+        fstride = T * H * W * {torch.float32: 4, torch.uint8: 1, torch.bfloat16: 2}[dtype]
+        k0, chunk, prev, ci = 0, 1, 0, 0
         while k0 < K:
+            if ramp is not None:
+                chunk = ramp[min(ci, len(ramp) - 1)]
+                ci += 1
             k1 = min(K, k0 + chunk)
+            nst = k1 - k0
+            fptrs, rows, fast, shared = [], [], fast_clip, t_frames[k0].size(0) == 1 and S > 1
             for k in range(k0, k1):
                 fr = frames[k]
                 if fr.shape != f0.shape or not fr.is_cuda:
@@ -871,33 +852,44 @@ class EventEmulatorBatch(nn.Module):
                 if fr.dtype != dtype:
                     fr = fr.to(dtype)
                 fr = fr.contiguous()
+                frames[k] = fr
                 keep.append(fr)
                 tf = t_frames[k]
-                shared = tf.size(0) == 1 and S > 1
-                fstride = fr.stride(0) * fr.element_size()
-                fbase = fr.data_ptr()
-                for g, (a, n, pl, ws) in enumerate(groups):
-                    pk = packs[g]
-                    for j in range(n):
-                        i = a + j
-                        em = self.emulators[i]
-                        # (a [T, H, W] view of the step's frames without a torch indexing op)
-                        fr_i = _FrameView(fbase + i * fstride, (T, H, W))
-                        vox = out_ptr + (k * S + i) * ostride
-                        mp = meta_ptr + 16 * (k * S + i)
-                        if shared and i > 0 and em._time_state_key() == key0:
-                            em._prep_pack_like(pk[k * n + j], fr_i, self.emulators[0], vox, mp)
-                        else:
-                            if i == 0:
-                                key0 = em._time_state_key()   # (before the step)
-                            em._prep_pack(pk[k * n + j], fr_i, tf if shared else tf[i:i + 1], vox, mp)
+                if fast and not (tf.dim() == 2 and tf.dtype == f64 and not tf.is_cuda
+                                 and tf.shape[1] == n_st and tf.is_contiguous()
+                                 and not tf.requires_grad
+                                 and tf.shape[0] == (1 if shared else S)):
+                    fast = False
+                fptrs.append(fr.data_ptr())
+                rows.append(tf.data_ptr() if fast else 0)
+            if fast:
+                fp_arr, row_arr = (C.c_void_p * nst)(*fptrs), (C.c_void_p * nst)(*rows)
             for g, (a, n, pl, ws) in enumerate(groups):
-                pk0 = C.cast(C.addressof(packs[g]) + k0 * n * C.sizeof(_cabi.Pack), C.POINTER(_cabi.Pack))
+                pk = packs[g]
+                for j in range(n):
+                    i = a + j
+                    em = self.emulators[i]
+                    done = False
+                    if fast:
+                        pk0 = C.cast(C.addressof(pk) + (k0 * n + j) * sizeof_pack, C.POINTER(_cabi.Pack))
+                        done = em._prep_chunk_c(pk0, nst, fp_arr, row_arr, n_st, T, H, W,
+                                                out_ptr + (k0 * S + i) * ostride, S * ostride,
+                                                meta_ptr + 16 * (k0 * S + i), 16 * S, i * fstride,
+                                                0 if shared else i * n_st * 8, n)
+                    if not done:      # pack by pack (raises what has to be raised)
+                        for k in range(k0, k1):
+                            tf = t_frames[k]
+                            sh = tf.size(0) == 1 and S > 1
+                            fr_i = _FrameView(fptrs[k - k0] + i * fstride, (T, H, W))
+                            em._prep_pack(pk[k * n + j], fr_i, tf if sh else tf[i:i + 1],
+                                          out_ptr + (k * S + i) * ostride, meta_ptr + 16 * (k * S + i))
+            for g, (a, n, pl, ws) in enumerate(groups):
+                pk0 = C.cast(C.addressof(packs[g]) + k0 * n * sizeof_pack, C.POINTER(_cabi.Pack))
                 ev0 = None
                 if evp is not None:
                     ev0 = C.cast(C.addressof(evp) + (g * 2 * K + 2 * k0) * C.sizeof(C.c_void_p),
                                  C.POINTER(C.c_void_p))
-                rc = lib.v2e_batch_clip_forward(C.byref(pl.cfg), pk0, k1 - k0, n, ws.data_ptr(),
+                rc = lib.v2e_batch_clip_forward(C.byref(pl.cfg), pk0, nst, n, ws.data_ptr(),
                                                 ws.numel(), stream, ev0)
                 _cabi.check(rc, "v2e_batch_clip_forward")
             k0, chunk, prev = k1, min(chunk + prev if prev else 1, 16), chunk
