@@ -52,11 +52,11 @@ EMU = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, s
            refractory_period_s=0.001, leak_rate_hz=0.1, shot_noise_rate_hz=1,
            pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)     # cfg2 params + model_v2e2v.py:56-57
 ALGO_BYTES_PER_PIXEL_PACK = 92      # 9 f32 frames + 5 f32 bins + 6 planes in + 3 planes out
-# measured DRAM bytes per PACK (ncu --set full: profiles/r02_k_fixpoint_spec_chain3_* for the
-# fixed-point engine - a chained launch of 3 packs, 127.9 MB read + 35.6 MB written; profiles/r01_*
+# measured DRAM bytes per PACK (ncu --set full: profiles/r02_k_fixpoint_spec_chain16_* for the
+# fixed-point engine - a chained launch of 16 packs, 600.6 MB read + 305.7 MB written; profiles/r01_*
 # for the others): (workload, noise, engine)
 TRAFFIC_BYTES = {("cfg3", "philox", "persistent"): 55447040 + 3553024,
-                 ("cfg3", "philox", "fixpoint"): (127863552 + 35626240) // 3,
+                 ("cfg3", "philox", "fixpoint"): (600577024 + 305681920) // 16,
                  ("cfg3", "off", "fixpoint"): 51731968 + 3537152}
 
 

@@ -17,6 +17,8 @@
  *     generate_shot_noise            v2e/emulator_utils.py:161-207          (fused)
  *     event_preprocess_pytorch       utils/event_process.py:157-177         (fused epilogue)
  *   forward() scalar prep            v2e/v2e_model.py:303-318,353           v2e_host_pack_scalars
+ *   the caller's pack loop           test.py:115-121, model_v2e2v.py:101    v2e_host_clip_prepare (host half),
+ *                                                                          v2e_clip_forward, v2e_batch_clip_forward
  *   events_to_voxel_grid[_pytorch]   utils/event_process.py:15-63,66-129  v2e_events_to_voxel
  *   event_preprocess[_pytorch]       utils/event_process.py:132-177       v2e_voxel_normalize
  *

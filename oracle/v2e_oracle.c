@@ -293,8 +293,9 @@ int v2e_oracle_pack(const v2e_config* cfg, const v2e_pack* pk, int threads) {
  * events_to_voxel_grid, utils/event_process.py:15-63 (numpy; torch_semantics = 0) and
  * events_to_voxel_grid_pytorch, :66-129 (torch_semantics = 1).  events: host [n,4] rows
  * (t,x,y,p) as f64 (events_f64) or f32; NOT mutated (the reference overwrites column 0 and maps
- * p == 0 to -1 in place).  voxel: host f32 [num_bins,H,W].  Accumulation is sequential in event
- * order in f32, like np.add.at / index_add_ on CPU.
+ * p == 0 to -1 in place).  voxel: host f32 [num_bins,H,W].  Accumulation is sequential in f32 - every
+ * left-bin add in event order, then every right-bin add - like the reference's two np.add.at /
+ * index_add_ calls on CPU.
  */
 int v2e_oracle_events_to_voxel(const void* events, int events_f64, int64_t n, int num_bins,
                                int width, int height, int torch_semantics, float* voxel) {
@@ -304,43 +305,58 @@ int v2e_oracle_events_to_voxel(const void* events, int events_f64, int64_t n, in
     if (n == 0) return V2E_OK;
     const double* e64 = (const double*)events;
     const float* e32 = (const float*)events;
-    if (events_f64) {
-        /* :33-40 in f64 */
-        const double first = e64[0], last = e64[4 * (n - 1)];
-        double dT = last - first;
-        if (dT == 0) dT = 1.0;
+    /* deltaT and the rescaled stamps in the events' dtype (:33-40 / :92-98) */
+    const double first64 = events_f64 ? e64[0] : 0, last64 = events_f64 ? e64[4 * (n - 1)] : 0;
+    double dT64 = last64 - first64;
+    if (dT64 == 0) dT64 = 1.0;
+    const float first32 = events_f64 ? 0 : e32[0], last32 = events_f64 ? 0 : e32[4 * (n - 1)];
+    float dT32 = last32 - first32;
+    if (dT32 == 0) dT32 = 1.0f;
+    /* every left-bin add in event order, then every right-bin add (:51-57 / :111-124) */
+    for (int side = 0; side < 2; ++side)
         for (int64_t k = 0; k < n; ++k) {
-            const double ts = (double)(num_bins - 1) * (e64[4 * k] - first) / dT;
-            const int64_t x = (int64_t)e64[4 * k + 1], y = (int64_t)e64[4 * k + 2];
-            double pol = e64[4 * k + 3];
+            double ts, x, y, pol;
+            if (events_f64) {
+                ts = (double)(num_bins - 1) * (e64[4 * k] - first64) / dT64;
+                x = e64[4 * k + 1]; y = e64[4 * k + 2]; pol = e64[4 * k + 3];
+            } else {
+                ts = (double)((float)(num_bins - 1) * (e32[4 * k] - first32) / dT32);   /* f32 ops */
+                x = e32[4 * k + 1]; y = e32[4 * k + 2]; pol = e32[4 * k + 3];
+            }
             if (pol == 0) pol = -1;
-            /* numpy: tis = ts.astype(uint) (truncation); torch: floor + `tis >= 0` guard */
-            const double tf = torch_semantics ? floor(ts) : trunc(ts);
-            const int64_t ti = (int64_t)tf;
-            const double d = ts - tf;
-            const float left = (float)(pol * (1.0 - d)), right = (float)(pol * d);
-            if (ti < 0) continue;
-            if (ti < num_bins) voxel[x + y * width + ti * P] += left;
-            if (ti + 1 < num_bins) voxel[x + y * width + (ti + 1) * P] += right;
+            const int64_t px = (int64_t)x + (int64_t)y * width;
+            if (!torch_semantics) {
+                /* numpy (:41-57): tis = ts.astype(uint) truncates; dts = ts - tis is float64 even
+                 * for f32 events (float32 - uint64 promotes); the values are float64 and
+                 * np.add.at adds them to the f32 grid in the (f32,f64)->f64 loop, rounding the
+                 * sum to f32 on the way back */
+                const double tf = trunc(ts);
+                const int64_t ti = (int64_t)tf;
+                const double d = ts - tf;
+                const double left = pol * (1.0 - d), right = pol * d;
+                if (ti < 0) continue;
+                if (side == 0 && ti < num_bins) {
+                    float* v = voxel + px + ti * P;
+                    *v = (float)((double)*v + left);
+                }
+                if (side == 1 && ti + 1 < num_bins) {
+                    float* v = voxel + px + (ti + 1) * P;
+                    *v = (float)((double)*v + right);
+                }
+            } else {
+                /* torch (:99-124): tis = floor(ts), dts = ts - tis in the events' dtype;
+                 * pols.float() * (1.0 - dts.float()) and pols.float() * dts.float() in f32;
+                 * index_add_ (CPU) adds in f32 in event order; `tis >= 0` guard */
+                const double tf = floor(ts);
+                const int64_t ti = (int64_t)tf;
+                const float d = events_f64 ? (float)(ts - tf) : (float)ts - (float)tf;
+                const float pf = (float)pol;
+                const float left = pf * (1.0f - d), right = pf * d;
+                if (ti < 0) continue;
+                if (side == 0 && ti < num_bins) voxel[px + ti * P] += left;
+                if (side == 1 && ti + 1 < num_bins) voxel[px + (ti + 1) * P] += right;
+            }
         }
-    } else {
-        const float first = e32[0], last = e32[4 * (n - 1)];
-        float dT = last - first;
-        if (dT == 0) dT = 1.0f;
-        for (int64_t k = 0; k < n; ++k) {
-            const float ts = (float)(num_bins - 1) * (e32[4 * k] - first) / dT;
-            const int64_t x = (int64_t)e32[4 * k + 1], y = (int64_t)e32[4 * k + 2];
-            float pol = e32[4 * k + 3];
-            if (pol == 0) pol = -1;
-            const float tf = torch_semantics ? floorf(ts) : truncf(ts);
-            const int64_t ti = (int64_t)tf;
-            const float d = ts - tf;
-            const float left = pol * (1.0f - d), right = pol * d;
-            if (ti < 0) continue;
-            if (ti < num_bins) voxel[x + y * width + ti * P] += left;
-            if (ti + 1 < num_bins) voxel[x + y * width + (ti + 1) * P] += right;
-        }
-    }
     return V2E_OK;
 }
 

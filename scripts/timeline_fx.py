@@ -13,8 +13,17 @@ if noise == "off":
     cfg.update(leak_rate_hz=0, shot_noise_rate_hz=0)
 em = EventEmulator(device="cuda", engine="fixpoint", noise_mode=noise, lazy_num_events=True, **cfg)
 T = 10
-for k, fr, tfr in gc.video(1, 5, T, H, W):
-    em(fr.cuda(), tfr)
+chain = int(os.environ.get("V2E_TL_CHAIN", "0"))   # > 0: packs go out as one warm-up pack + chains of this length
+vid = list(gc.video(1, 5 if not chain else 1 + 3 * chain, T, H, W))
+steps = [(k, [fr], [tfr]) for k, fr, tfr in vid] if not chain else \
+    [(0, [vid[0][1]], [vid[0][2]])] + [(1 + c * chain, [v[1] for v in vid[1 + c * chain:1 + (c + 1) * chain]],
+                                        [v[2] for v in vid[1 + c * chain:1 + (c + 1) * chain]]) for c in range(3)]
+for k, frs, tfrs in steps:
+    if chain:
+        em.clip_ramp = (16,)
+        em.forward_clip([f.cuda()[0] for f in frs], tfrs)
+    else:
+        em(frs[0].cuda(), tfrs[0])
     torch.cuda.synchronize()
     ws = em._workspace
     tl = ws[ws.numel() - (160 * 32 * 8 + 2048 + 1024):].view(torch.int64).cpu().numpy()[:160 * 32].reshape(160, 32)

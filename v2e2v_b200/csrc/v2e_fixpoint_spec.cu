@@ -1427,7 +1427,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         }
     }
     FX_STAMP(31);
-    if (tl) {
+    if (tl && pk == min(2, prm.n_chain - 1)) {   // (a chain reports its third pack: one in steady state)
         __syncthreads();
         if (tid < 32) tl_out[tid] = tl[tid];
     }
