@@ -67,6 +67,36 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def nvml_handle(index: int):
+    """NVML handle of the CUDA device `index` of this process (LOCAL_RANK indexes
+    CUDA_VISIBLE_DEVICES; NVML wants the physical device)."""
+    import pynvml as nv
+    nv.nvmlInit()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        tok = vis.split(",")[index].strip()
+        return nv.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else \
+            nv.nvmlDeviceGetHandleByIndex(int(tok))
+    return nv.nvmlDeviceGetHandleByIndex(index)
+
+
+def bind_near_gpu(index: int):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) before any host buffer
+    exists: with one rank per GPU the pinned frame buffers of `e2e` then sit in the GPU's own NUMA
+    node instead of wherever the launcher started the rank.  Returns what was done (for `config`)."""
+    # opt-in (BENCH_BIND=1): on the single-NUMA-node boxes of this pool it changes nothing
+    # (e2e at 8 GPUs 51.6 vs 51.1 Gpx-frames/s: the host side tops out at ~185 GB/s of aggregate
+    # H2D traffic either way), and a bound rank would also confine the cpu_baseline's threads
+    if not os.environ.get("BENCH_BIND"):
+        return "off"
+    try:
+        import pynvml as nv
+        nv.nvmlDeviceSetCpuAffinity(nvml_handle(index))
+        return f"{len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:      # (restricted cpusets, no NVML: run unbound)
+        return f"unavailable ({type(e).__name__})"
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons while the timed regions run: NVML in-process (the
     rank's own GPU, every 10 ms - spawning nvidia-smi from every rank every 50 ms stalled other
@@ -83,16 +113,7 @@ class ClockSampler(threading.Thread):
     def _nvml_loop(self) -> bool:
         try:
             import pynvml as nv
-            nv.nvmlInit()
-            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML wants the physical device
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = self.index
-            if vis:
-                tok = vis.split(",")[self.index].strip()
-                h = nv.nvmlDeviceGetHandleByUUID(tok) if tok.startswith("GPU-") else \
-                    nv.nvmlDeviceGetHandleByIndex(int(tok))
-            else:
-                h = nv.nvmlDeviceGetHandleByIndex(idx)
+            h = nvml_handle(self.index)
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
             bits = [(nv.nvmlClocksEventReasonHwSlowdown, 0), (nv.nvmlClocksEventReasonHwThermalSlowdown, 1),
                     (nv.nvmlClocksEventReasonSwThermalSlowdown, 2), (nv.nvmlClocksEventReasonSwPowerCap, 3)]
@@ -165,6 +186,7 @@ def stamps(k):
 # -----------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     from v2e2v_b200 import EventEmulator, EventEmulatorBatch, _cabi
+    binding = bind_near_gpu(local_rank)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     H, W, S, desc = WORKLOADS[args.workload]
@@ -347,6 +369,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"{args.workload}: {desc}", "height": H, "width": W,
                    "num_pack_frames": T_FRAMES, "fps": FPS, "sequences_per_gpu": S,
                    "parallelism": f"{world} x independent sequence shard(s), no collective",
+                   "cpu_binding": binding,
                    "emulator": EMU, "noise_mode": args.noise, "philox_rounds": args.philox_rounds,
                    "engine": ems[0].resolved_engine, "frame_dtype": "f32", "voxel_dtype": "f32",
                    "l2_policy": f"inputs larger than L2: ring of {ring} distinct packs "
