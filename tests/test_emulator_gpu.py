@@ -518,6 +518,72 @@ def test_time_order_error_and_reset():
     assert v.shape == (1, 5, 16, 16)
 
 
+@pytest.mark.parametrize("layout", ["f64_rows", "two_col"])
+def test_forward_clip_time_order_error_mid_clip(layout):
+    """A clip whose 4th pack goes back in time: like the caller's loop around the reference
+    (test.py:115-121, v2e_model.py:335) the three packs before it are emulated, then ValueError
+    surfaces; state, time and Philox stream continue exactly where a per-pack loop would be.
+    Both preparation paths: float64 stamp rows (one C call per chunk) and 2-column stamps (the
+    torch-literal path, pack by pack)."""
+    cfg, H, W, T, K = gc.CFG2, 64, 96, 10, 6
+    pos, neg, nra = gc.make_planes(31, H, W, cfg)
+    two = layout == "two_col"
+    vids = [(fr.cuda(), tfr) for _, fr, tfr in gc.video(9, K, T, H, W, two_col=two)]
+    bad = [v[1] for v in vids]
+    bad[3] = vids[1][1]                       # pack 3 carries the stamps of pack 1
+    ems = []
+    for clip in (False, True):
+        em = gc.cuda_emulator(cfg, "auto", noise_mode="philox")
+        em.philox_seed = 5
+        em.set_planes(pos, neg, nra)
+        ems.append(em)
+        if clip:
+            with pytest.raises(ValueError, match="must be later than previous"):
+                em.forward_clip([v[0] for v in vids], bad)
+        else:
+            for k in range(3):
+                em(vids[k][0], vids[k][1])
+            with pytest.raises(ValueError, match="must be later than previous"):
+                em(vids[3][0], bad[3])
+    a, b = ems
+    torch.cuda.synchronize()
+    assert a.t_previous == b.t_previous
+    np.testing.assert_array_equal(a.base_log_frame.cpu().numpy(), b.base_log_frame.cpu().numpy())
+    np.testing.assert_array_equal(a.timestamp_mem.cpu().numpy(), b.timestamp_mem.cpu().numpy())
+    # both carry on identically with the right pack
+    va, na = a(vids[3][0], vids[3][1])
+    vb, nb_ = b(vids[3][0], vids[3][1])
+    assert na == nb_
+    np.testing.assert_array_equal(va.cpu().numpy(), vb.cpu().numpy())
+
+
+def test_forward_clip_one_more_stamp_than_frames():
+    """What test.py feeds after the first pack (video_readers.py:85-86,100-101): T-1 frames with T
+    stamps - frame n pairs with stamp n, the last stamp only enters Tr (v2e_model.py:317).  The C
+    preparation of a clip == the per-pack loop on that layout."""
+    cfg, H, W, T, K = gc.CFG2, 64, 96, 10, 5
+    pos, neg, nra = gc.make_planes(32, H, W, cfg)
+    vids = [(fr[:, :T - 1].contiguous().cuda(), tfr) for _, fr, tfr in gc.video(10, K, T, H, W)]
+    res = []
+    for clip in (False, True):
+        em = gc.cuda_emulator(cfg, "auto", noise_mode="philox")
+        em.philox_seed = 6
+        em.set_planes(pos, neg, nra)
+        if clip:
+            vox, nev = em.forward_clip([v[0] for v in vids], [v[1] for v in vids])
+            em.check_status()
+            nev = nev.tolist()
+        else:
+            outs = [em(fr, tfr) for fr, tfr in vids]
+            vox, nev = torch.cat([o[0] for o in outs]), [o[1] for o in outs]
+        res.append((vox.cpu().numpy(), nev, em.base_log_frame.cpu().numpy(),
+                    em.timestamp_mem.cpu().numpy(), em.t_previous))
+    a, b = res
+    assert a[1] == b[1] and sum(a[1]) > 0 and a[4] == b[4]
+    for i in (0, 2, 3):
+        np.testing.assert_array_equal(a[i], b[i])
+
+
 def test_b_gt_1_rejected_and_cpu_tensor_rejected():
     em = gc.cuda_emulator(dict(gc.CFG2, leak_rate_hz=0, shot_noise_rate_hz=0), "auto")
     t = torch.tensor([[0.0, 0.003]], dtype=torch.float64)

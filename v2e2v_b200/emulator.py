@@ -510,14 +510,24 @@ class EventEmulator(nn.Module):
                 fast = self._prep_chunk_c(pk0, n, (C.c_void_p * n)(*fptrs), (C.c_void_p * n)(*rows),
                                           n_st, num_frames, height, width,
                                           out_ptr + k0 * ostride, ostride, meta_ptr + 16 * k0)
+            failed = None
             if not fast:
-                for k in range(k0, k1):
-                    if k:
-                        frames[k] = norm(frames[k])
-                        if frames[k].shape != shp0 or frames[k].dtype != dt0:
-                            raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
-                    self._prep_pack(packs[k], frames[k], t_frames[k], out_ptr + k * ostride,
-                                    meta_ptr + 16 * k)
+                k = k0
+                try:
+                    for k in range(k0, k1):
+                        if k:
+                            frames[k] = norm(frames[k])
+                            if frames[k].shape != shp0 or frames[k].dtype != dt0:
+                                raise ValueError("forward_clip needs K >= 1 packs of one shape and dtype")
+                        self._prep_pack(packs[k], frames[k], t_frames[k], out_ptr + k * ostride,
+                                        meta_ptr + 16 * k)
+                except Exception as e:
+                    # like the caller's loop around the reference (test.py:115-121): the packs
+                    # before the offending one are emulated, then the error surfaces
+                    failed, n = e, k - k0
+            if failed is not None and n == 0:
+                self._clip_keep = (frames, packs)
+                raise failed
             ev0 = None
             if evp is not None:
                 ev0 = C.cast(C.addressof(evp) + 2 * k0 * sizeof_vp, C.POINTER(C.c_void_p))
@@ -528,6 +538,9 @@ class EventEmulator(nn.Module):
             _cabi.check(rc, "v2e_clip_forward")
             if tr is not None:
                 tr.append((f"enqueue {n}", _t.perf_counter()))
+            if failed is not None:
+                self._clip_keep = (frames, packs)
+                raise failed
             k0, chunk, prev = k1, min(chunk + prev if prev else 1, 16), chunk
         self._clip_keep = (frames, packs)       # keep the inputs alive until the stream is done
         meta32 = meta.view(torch.int32)         # [K, 4]: num_events lo/hi, status, pad
