@@ -109,6 +109,10 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._halt = index, [], threading.Event()
         self.source = None
         self.period = float(os.environ.get("BENCH_SAMPLER_MS", "10")) * 1e-3
+        self._paused = threading.Event()
+        self.ready = threading.Event()     # NVML is up (or the fall-back was chosen)
+        self._nv = None          # (module, handle, max clock, reason bits) once NVML is up
+        self.in_region = 0       # samples taken by sample_now() while the timed region ran
 
     def _nvml_loop(self) -> bool:
         try:
@@ -122,22 +126,51 @@ class ClockSampler(threading.Thread):
         except Exception:
             return False
         self.source = "nvml"
+        self._nv = (nv, h, mx, bits)
+        self.ready.set()
         while not self._halt.is_set():
-            try:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
-            except Exception:
-                pass
+            if not self._paused.is_set():
+                self._sample()
             self._halt.wait(self.period)
         return True
 
+    def _sample(self) -> bool:
+        if self._nv is None:
+            return False
+        nv, h, mx, bits = self._nv
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b, _ in bits])
+            return True
+        except Exception:
+            return False
+
+    def pause(self):
+        """No background sample (a second thread taking the GIL, an NVML call inside the driver)
+        while the host enqueues the short timed region; `sample_now` covers it instead."""
+        self._paused.set()
+
+    def resume(self):
+        self._paused.clear()
+
+    def sample_now(self, still_running) -> None:
+        """Samples from the calling thread while `still_running()` (the timed region's work is
+        all enqueued and the device is executing it: nothing is delayed)."""
+        for _ in range(8):
+            if not still_running():
+                break
+            if self._sample():
+                self.in_region += 1
+
     def run(self):
         if os.environ.get("BENCH_NO_SAMPLER"):     # development aid
+            self.ready.set()
             return
         if not os.environ.get("BENCH_SAMPLER_SMI") and self._nvml_loop():
             return
         self.source = "nvidia-smi"
+        self.ready.set()
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -159,7 +192,8 @@ class ClockSampler(threading.Thread):
         mx = max([int(r[1]) for r in self.rows if r[1].isdigit()] or [0])
         reasons = sorted({n for r in self.rows for n, v in zip(self.NAMES, r[2:]) if v == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": reasons, "samples": len(self.rows), "source": self.source}
+                "reasons": reasons, "samples": len(self.rows),
+                "samples_inside_value_region": self.in_region, "source": self.source}
 
 
 def synth_pack_device(gen, base, H, W, dtype=torch.float32):
@@ -275,12 +309,16 @@ def run_ours(args, rank, world, local_rank):
     clip_ev.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gc.disable()        # no collector pause between two enqueues of the timed region
+    sampler.ready.wait(5.0)
+    sampler.pause()     # ... and no second thread: the region is sampled below, once it is enqueued
     barrier()
     launches0 = lib.v2e_launch_count()
     e0.record()
     k = run_clips(k, K)
     e1.record()
+    sampler.sample_now(lambda: not e1.query())   # clocks / throttle reasons while the region runs
     barrier()
+    sampler.resume()
     gc.enable()
     if batch is not None:
         batch.check_status()
