@@ -378,6 +378,40 @@ def test_batch_forward_clip_equals_step_loop(S, shared):
         np.testing.assert_array_equal(a[3][s], b[3][s])
 
 
+def test_batch_full_size_64_sequences():
+    """BASELINE configs[3] at full size: 64 sequences of 346x260 in one EventEmulatorBatch (four
+    launch groups of 16), two steps through forward_clip.  Sampled sequences == separate
+    emulators bit for bit (states, counts) / within tolerance (voxel); every sequence's normalised
+    grid has mean 0 / std 1 on its non-zeros (statistics never mix sequences)."""
+    from v2e2v_b200 import EventEmulator, EventEmulatorBatch
+    cfg, H, W, T, S, K = gc.CFG2, 260, 346, 10, 64, 2
+    planes = gc.make_planes(200, H, W, cfg)
+    batch = EventEmulatorBatch(S, device="cuda", noise_mode="philox", **cfg)
+    vids = [list(gc.video(300 + s, K, T, H, W)) for s in range(S)]
+    for s in range(S):
+        batch[s].set_planes(*planes)
+    frames = [torch.cat([vids[s][k][1] for s in range(S)]).to(torch.uint8).cuda() for k in range(K)]
+    vox, nev = batch.forward_clip(frames, [vids[0][k][2] for k in range(K)])
+    batch.check_status()
+    assert vox.shape == (K, S, cfg["num_bins"], H, W) and int(nev.min().item()) > 0
+    for s in (0, 15, 16, 37, 63):
+        em = EventEmulator(device="cuda", noise_mode="philox", **cfg)
+        em.philox_seed = batch[s].philox_seed
+        em.set_planes(*planes)
+        for k in range(K):
+            v1, n1 = em(vids[s][k][1].to(torch.uint8).cuda(), vids[s][k][2])
+            assert int(nev[k, s].item()) == n1, (k, s)
+            np.testing.assert_allclose(vox[k, s].cpu().numpy(), v1[0].cpu().numpy(),
+                                       rtol=VOX_RTOL, atol=VOX_ATOL)
+        np.testing.assert_array_equal(batch[s].base_log_frame.cpu().numpy(), em.base_log_frame.cpu().numpy())
+        np.testing.assert_array_equal(batch[s].timestamp_mem.cpu().numpy(), em.timestamp_mem.cpu().numpy())
+    v = vox[K - 1].double().reshape(S, -1)
+    nz = v != 0
+    mean = (v * nz).sum(1) / nz.sum(1)
+    var = ((v - mean[:, None]) ** 2 * nz).sum(1) / nz.sum(1)
+    assert float(mean.abs().max()) < 1e-4 and float((var.sqrt() - 1).abs().max()) < 1e-4
+
+
 @pytest.mark.parametrize("T,nb,vdt", [(14, 5, torch.float32), (10, 3, torch.float32),
                                       (7, 8, torch.float32), (10, 5, torch.bfloat16)])
 def test_fixpoint_other_pack_shapes(T, nb, vdt):
