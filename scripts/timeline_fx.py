@@ -11,7 +11,8 @@ noise = sys.argv[3] if len(sys.argv) > 3 else "philox"
 cfg = dict(gc.CFG2)
 if noise == "off":
     cfg.update(leak_rate_hz=0, shot_noise_rate_hz=0)
-em = EventEmulator(device="cuda", engine="fixpoint", noise_mode=noise, lazy_num_events=True, **cfg)
+em = EventEmulator(device="cuda", engine="fixpoint", noise_mode=noise, lazy_num_events=True,
+                   philox_rounds=int(os.environ.get("V2E_TL_ROUNDS", "10")), **cfg)
 T = 10
 chain = int(os.environ.get("V2E_TL_CHAIN", "0"))   # > 0: packs go out as one warm-up pack + chains of this length
 vid = list(gc.video(1, 5 if not chain else 1 + 3 * chain, T, H, W))
