@@ -354,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
     pack_ms = [sum(ev[g][2 * j].elapsed_time(ev[g][2 * j + 1]) for g in range(G)) for j in range(KR)]
     launch_ms, launch_packs = [], []
     for d in pack_ms:
-        if d > 0.01 or not launch_ms:
+        if d > 0.01 * G or not launch_ms:     # (an empty interval is two event records per group)
             launch_ms.append(d)
             launch_packs.append(1)
         else:

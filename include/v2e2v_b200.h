@@ -262,8 +262,10 @@ int v2e_clip_forward(const v2e_config* cfg, const v2e_pack* packs, int n_packs,
 
 /* -- a clip of a batch: consecutive steps of n_seq independent sequences in one call -------------
  * packs[i * n_seq + s] is pack i of sequence s (s < n_seq <= V2E_MAX_SEQ_PER_LAUNCH); step i is
- * one v2e_pack_forward(packs + i * n_seq, n_seq) launch, enqueued in order on `stream` with no
- * host work in between (the reference runs the sequences of a batch one emulator after the other,
+ * what v2e_pack_forward(packs + i * n_seq, n_seq) does; consecutive steps are chained into one
+ * launch when the specialised fixed-point kernel serves the request (up to 128 pack records per
+ * launch: 16 steps of 8 sequences, 8 steps of 16), otherwise one launch per step, enqueued in
+ * order on `stream` with no host work in between (the reference runs the sequences of a batch one emulator after the other,
  * one pack at a time: configs.py:62-63, test.py:115-121).  events: optional 2*n_packs
  * cudaEvent_t, recorded before and after each step (NULL: none). */
 int v2e_batch_clip_forward(const v2e_config* cfg, const v2e_pack* packs, int n_packs, int n_seq,

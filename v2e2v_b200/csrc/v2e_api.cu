@@ -219,7 +219,39 @@ int v2e_batch_clip_forward(const v2e_config* c, const v2e_pack* packs, int n_pac
                            void* const* events) {
     if (!packs || n_packs < 1 || n_seq < 1 || n_seq > V2E_MAX_SEQ_PER_LAUNCH) return V2E_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int i = 0; i < n_packs; ++i) {
+    // Chains, as in v2e_clip_forward: consecutive steps go out as ONE launch when the specialised
+    // fixed-point kernel serves the request (as many steps as the launch-record ring holds).
+    static const bool no_chain = getenv("V2E_NO_CHAIN") != nullptr;   // development aid
+    CfgDev cfg;
+    int i0 = 0;
+    if (!no_chain && n_packs > 1 && make_cfg(c, cfg) == V2E_OK && workspace && aligned16(workspace) &&
+        workspace_bytes >= step_layout(cfg, n_seq).total &&
+        v2e_resolve_engine(c, n_seq) == V2E_ENGINE_FIXPOINT) {
+        const int rounds = c->philox_rounds == 7 ? 7 : 10;
+        int cap = 128 / n_seq;     // (kFxBlkSlots records per launch)
+        if (cap > V2E_MAX_SEQ_PER_LAUNCH) cap = V2E_MAX_SEQ_PER_LAUNCH;
+        while (cap > 1 && n_packs - i0 > 1) {
+            const int m = n_packs - i0 < cap ? n_packs - i0 : cap;
+            const int T = packs[(size_t)i0 * n_seq].sc.num_frames;
+            bool ok = T >= 2 && T <= V2E_MAX_FRAMES;
+            for (int j = 0; ok && j < m * n_seq; ++j)
+                ok = check_pack(cfg, packs[(size_t)i0 * n_seq + j], T) == V2E_OK;
+            if (!ok) break;   // (the per-step path reports what is wrong)
+            const int rc = run_fixpoint(cfg, c->frame_dtype, rounds, packs + (size_t)i0 * n_seq, n_seq,
+                                        workspace, st, m, events ? events[2 * i0] : nullptr);
+            if (rc == V2E_ERR_UNSUPPORTED) break;   // nothing was enqueued: one launch per step below
+            if (rc != V2E_OK) return rc;
+            if (events)      // the first step's pair brackets the launch, the others are empty intervals
+                for (int j = 0; j < m; ++j) {
+                    void* const e1 = events[2 * (i0 + j) + 1];
+                    void* const e0 = j + 1 < m ? events[2 * (i0 + j + 1)] : nullptr;
+                    if (e1 && cuda_ok(cudaEventRecord((cudaEvent_t)e1, st)) != V2E_OK) return V2E_ERR_CUDA;
+                    if (e0 && cuda_ok(cudaEventRecord((cudaEvent_t)e0, st)) != V2E_OK) return V2E_ERR_CUDA;
+                }
+            i0 += m;
+        }
+    }
+    for (int i = i0; i < n_packs; ++i) {
         if (events && events[2 * i]) {
             const int rc = cuda_ok(cudaEventRecord((cudaEvent_t)events[2 * i], st));
             if (rc != V2E_OK) return rc;

@@ -66,8 +66,8 @@ inline StepLayout step_layout(const CfgDev& cfg, int n_seq) {
     l.vox_off = up(sizeof(SeqWork) * (size_t)n_seq);
     l.cntpol_off = up(l.vox_off + (size_t)n_seq * cfg.nb * cfg.P * sizeof(float));
     l.fx_off = up(l.cntpol_off + (size_t)n_seq * cfg.P * sizeof(int));
-    // (two sets of barrier words for a single sequence: the packs of a chain alternate)
-    l.fxstate_off = up(l.fx_off + sizeof(FxWork) * (size_t)(n_seq > 2 ? n_seq : 2));
+    // (two sets of barrier words per sequence, [set][seq]: the packs of a chain alternate)
+    l.fxstate_off = up(l.fx_off + sizeof(FxWork) * (size_t)(2 * n_seq));
     l.fxblk_off = up(l.fxstate_off + (size_t)n_seq * 3 * cfg.P * sizeof(float));
     l.tl_off = up(l.fxblk_off + kFxBlkBytes);
     l.total = up(l.tl_off + kTimelineBytes);
@@ -145,8 +145,8 @@ int run_runahead(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack*
 // 1 if the persistent / run-ahead engine can hold n_seq sequences of this config on chip
 int persistent_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
 int runahead_fits(const CfgDev& cfg, int frame_dtype, int n_seq);
-// n_chain > 1: one launch for n_chain consecutive packs of one sequence (V2E_ERR_UNSUPPORTED, with
-// nothing enqueued, when the request does not qualify); ev_launch: optional cudaEvent_t recorded
+// n_chain > 1: one launch for n_chain consecutive packs of each of the n_seq sequences,
+// packs[i * n_seq + s] (V2E_ERR_UNSUPPORTED, with nothing enqueued, when the request does not qualify); ev_launch: optional cudaEvent_t recorded
 // right before the kernel launch (after the launch records were copied)
 int run_fixpoint(const CfgDev& cfg, int frame_dtype, int rounds, const v2e_pack* packs, int n_seq,
                  void* workspace, cudaStream_t st, int n_chain = 1, void* ev_launch = nullptr);

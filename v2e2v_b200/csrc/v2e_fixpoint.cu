@@ -37,6 +37,8 @@
 // workspace until commit.  Slower, same results.
 #include <cstring>
 
+#include <vector>
+
 #include "v2e_fixpoint.cuh"
 
 namespace v2e {
@@ -772,22 +774,23 @@ static int launch_fixpoint(const FxParams& prm, const FxPlan& pl, cudaStream_t s
     return launch_fixpoint_v<FDT, R, NOISE, CUTOFF, false>(prm, pl, st);
 }
 
-// n_chain > 1: packs[0..n_chain) are consecutive packs of ONE sequence (n_seq == 1), served by one
-// launch of the specialised kernel; V2E_ERR_UNSUPPORTED (before anything is enqueued) when the
-// request does not qualify - the caller then launches them one by one.
+// n_chain > 1: packs[i * n_seq + s], i < n_chain, are consecutive packs of sequence s, all served by
+// one launch of the specialised kernel; V2E_ERR_UNSUPPORTED (before anything is enqueued) when the
+// request does not qualify - the caller then launches step by step.
 template <int FDT>
 static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, int n_seq,
                           void* workspace, cudaStream_t st, int n_chain, void* ev_launch) {
     const FxPlan pl = fx_plan(cfg, n_seq, packs[0].sc.num_frames);
     if (!pl.ok) return V2E_ERR_UNSUPPORTED;
-    const int n_blk = n_chain > 1 ? n_chain : n_seq;
+    const int n_blk = (n_chain > 1 ? n_chain : 1) * n_seq;
     if (n_chain > 1) {
-        if (n_seq != 1 || n_chain > V2E_MAX_SEQ_PER_LAUNCH || !pl.spec) return V2E_ERR_UNSUPPORTED;
-        for (int s = 0; s < n_chain; ++s) {
-            const v2e_pack& p = packs[s];
-            if (p.sc.num_frames != packs[0].sc.num_frames || p.base_log_frame != packs[0].base_log_frame ||
-                p.lp_log_frame0 != packs[0].lp_log_frame0 || p.timestamp_mem != packs[0].timestamp_mem || p.pos_thres != packs[0].pos_thres ||
-                p.neg_thres != packs[0].neg_thres || p.noise_rate != packs[0].noise_rate ||
+        if (n_chain > V2E_MAX_SEQ_PER_LAUNCH || n_blk > kFxBlkSlots || !pl.spec) return V2E_ERR_UNSUPPORTED;
+        for (int b = 0; b < n_blk; ++b) {
+            const v2e_pack& p = packs[b];
+            const v2e_pack& q = packs[b % n_seq];     // the sequence's first pack of the chain
+            if (p.sc.num_frames != packs[0].sc.num_frames || p.base_log_frame != q.base_log_frame ||
+                p.lp_log_frame0 != q.lp_log_frame0 || p.timestamp_mem != q.timestamp_mem || p.pos_thres != q.pos_thres ||
+                p.neg_thres != q.neg_thres || p.noise_rate != q.noise_rate ||
                 p.dbg_pol || p.dbg_cnt || p.dbg_final || p.dbg_leak_randn || p.dbg_shot)
                 return V2E_ERR_UNSUPPORTED;
         }
@@ -810,8 +813,10 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     static const bool want_timeline = getenv("V2E_TIMELINE") != nullptr;
     prm.timeline = want_timeline ? (long long*)((char*)workspace + lay.tl_off) : nullptr;
     bool dbg = false;
-    static thread_local FxSeqBlock stage[V2E_MAX_SEQ_PER_LAUNCH];
+    static thread_local std::vector<FxSeqBlock> stage_v;
     static thread_local unsigned ring_pos = 0;
+    if ((int)stage_v.size() < n_blk) stage_v.resize(n_blk);
+    FxSeqBlock* const stage = stage_v.data();
     for (int s = 0; s < n_blk; ++s) {
         FxSeqBlock& b = n_blk == 1 ? prm.one : stage[s];
         fill_seq(b.sq, packs[s]);
@@ -831,7 +836,7 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     if (n_chain > 1 && noise == 2) return V2E_ERR_UNSUPPORTED;   // (nothing has been enqueued yet)
     prm.blocks = nullptr;
     prm.fr_in_params = n_blk == 1;
-    if (n_chain > 1) {
+    if (n_chain > 1 && n_seq == 1) {
         // a chain whose packs share the stream pass's frame scalars bit for bit (evenly spaced
         // stamps: the usual case) keeps them in the kernel parameters, like a single pack
         bool same = true;
@@ -849,11 +854,18 @@ static int run_fixpoint_t(const CfgDev& cfg, int rounds, const v2e_pack* packs, 
     if (n_blk > 1) {
         // the records of a multi-sequence launch or a chain go through the workspace, copied in stream order
         // (a ring of slots: the copy for launch i+1 never touches what launch i is reading)
-        FxSeqBlock* slot = (FxSeqBlock*)((char*)workspace + lay.fxblk_off) +
-                           (size_t)(ring_pos++ % kFxBlkRing) * V2E_MAX_SEQ_PER_LAUNCH;
-        const int rc = cuda_ok(cudaMemcpyAsync(slot, stage, sizeof(FxSeqBlock) * n_blk,
-                                               cudaMemcpyHostToDevice, st));
-        if (rc != V2E_OK) return rc;
+        if (ring_pos + (unsigned)n_blk > (unsigned)kFxBlkSlots) ring_pos = 0;
+        FxSeqBlock* slot = (FxSeqBlock*)((char*)workspace + lay.fxblk_off) + ring_pos;
+        ring_pos += (unsigned)n_blk;
+        // (pieces of at most 32 KB: small copies from pageable memory are staged by the driver at
+        // once and never wait for the stream)
+        const int per = (int)(32768 / sizeof(FxSeqBlock));
+        for (int b0 = 0; b0 < n_blk; b0 += per) {
+            const int nb_ = n_blk - b0 < per ? n_blk - b0 : per;
+            const int rc = cuda_ok(cudaMemcpyAsync(slot + b0, stage + b0, sizeof(FxSeqBlock) * nb_,
+                                                   cudaMemcpyHostToDevice, st));
+            if (rc != V2E_OK) return rc;
+        }
         prm.blocks = slot;
     }
     if (ev_launch) {   // (timing aid: after the record copy, right before the kernel)

@@ -47,8 +47,11 @@ struct FxSeqBlock {
     SeqDev sq;
     FrameSc fr[V2E_MAX_FRAMES];
 };
-constexpr int kFxBlkRing = 8;   // launches whose records may be in flight in the workspace
-static_assert(sizeof(FxSeqBlock) <= 1280 && kFxBlkRing * V2E_MAX_SEQ_PER_LAUNCH * 1280 <= kFxBlkBytes,
+// launch records in the workspace: a circular buffer of kFxBlkSlots records; a launch takes
+// n_chain * n_seq consecutive ones (copied in stream order, so the copy for a launch never
+// overtakes the launch before it; consecutive launches use disjoint ranges whenever two fit)
+constexpr int kFxBlkSlots = 128;
+static_assert(sizeof(FxSeqBlock) <= 1280 && kFxBlkSlots * 1280 <= kFxBlkBytes,
               "workspace ring too small (v2e_engine.cuh, kFxBlkBytes)");
 
 // Kernel parameters stay well under 4 KB: the launch path for larger parameter blocks costs
@@ -66,7 +69,7 @@ struct FxParams {
     float* spill_state;    // [n_seq][3][P]  base, lp, tmem results of spilled pixels
     long long* timeline;   // development aid (V2E_TIMELINE=1): [cta][32] globaltimer stamps
     int fr_in_params;  // one.fr and the plane pointers of one.sq are valid for every pack of this launch
-    int n_chain;       // consecutive packs of the one sequence served by this launch (n_seq == 1), else 1
+    int n_chain;       // consecutive packs of every sequence served by this launch (records [pack][seq])
     const FxSeqBlock* blocks;   // n_seq > 1 or a chain: records in the workspace (copied there in stream order)
     FxSeqBlock one;             // n_seq == 1: the record travels with the parameters
 };

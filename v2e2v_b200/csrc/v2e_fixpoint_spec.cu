@@ -360,14 +360,14 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seq = blockIdx.x / prm.tiles_per_seq;
     const int tile = blockIdx.x - seq * prm.tiles_per_seq;
-    // A launch serves one pack of n_seq sequences, or a chain of n_chain consecutive packs of one
-    // sequence (the caller's pack loop, test.py:115-121, in one launch: every CTA keeps its tile,
+    // A launch serves one pack of n_seq sequences, or a chain of n_chain consecutive packs of each
+    // of them (the caller's pack loop, test.py:115-121, in one launch: every CTA keeps its tile,
     // the state planes carry over in place, and neither the launch gap nor the set-up is paid
     // again).  Consecutive packs of a chain alternate between two sets of barrier words, so that
     // the last CTA to leave a pack can zero its set while the others are already in the next.
     for (int pk = 0; pk < prm.n_chain; ++pk) {
     // this pack's launch record -> shared memory
-    const FxSeqBlock* blk = prm.blocks ? prm.blocks + seq + pk : &prm.one;
+    const FxSeqBlock* blk = prm.blocks ? prm.blocks + (size_t)pk * prm.n_seq + seq : &prm.one;
     {
         unsigned* d_sq = (unsigned*)(smem_raw + 3840);
         const unsigned* s_sq = (const unsigned*)&blk->sq;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     // parameters when they hold it (ONE): constant-bank operands instead of shared-memory loads
     // that would be repeated after every table store
     const SeqDev& sqc = ONE ? prm.one.sq : sq;
-    FxWork& fx = prm.fx[seq + (pk & 1)];
+    FxWork& fx = prm.fx[seq + (pk & 1) * prm.n_seq];
     FxWork& fx0 = prm.fx[seq];   // holds the hint for the launch that follows
     const int P = cfg.P;
     const bool normalise = cfg.output_mode == V2E_OUT_VOXEL;
