@@ -232,8 +232,9 @@ def run_ours(args, rank, world, local_rank):
         from v2e2v_b200.sharding import shard_sequences
         S = len(shard_sequences(-S, rank, world))      # this rank's contiguous block
     K, Wm = args.steps, max(args.warmup, 3)
-    ring = max(2, -(-160_000_000 // (H * W * T_FRAMES * 4 * S)))   # > L2 (126 MB) of inputs
-    ring = min(ring, 16)
+    fbytes = 1 if args.frames == "u8" else 4
+    ring = max(2, -(-160_000_000 // (H * W * T_FRAMES * fbytes * S)))   # > L2 (126 MB) of inputs
+    ring = min(ring, 16 if fbytes == 4 else 20)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     torch.manual_seed(rank)
     ems, packs = [], []
@@ -255,6 +256,10 @@ def run_ours(args, rank, world, local_rank):
             seqp.append(fr)
         packs.append(seqp)
     pinned = [[p.cpu().pin_memory() for p in seqp] for seqp in packs]
+    if args.frames == "u8":
+        # the device-resident frames as the reference's readers hold them before .float() (lossless:
+        # integer-valued 0..255; bit-identical results); `e2e` keeps its f32 host frames
+        packs = [[p.to(torch.uint8) for p in seqp] for seqp in packs]
     # [S, T, H, W] per ring slot for the batched launches
     bpacks = ([torch.cat([packs[s][r] for s in range(S)]) for r in range(ring)]
               if batch is not None else None)
@@ -405,9 +410,10 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = peaks()
     # one timed interval = one step = one pack of each of the rank's S sequences (S = 1: one
     # pack; S > 1: one batched launch)
-    algo_bytes = ALGO_BYTES_PER_PIXEL_PACK * H * W * S
+    # (uint8 frames: 9 B of frames per pixel and pack instead of 36 - SURVEY 8d's 65 B figure)
+    algo_bytes = (ALGO_BYTES_PER_PIXEL_PACK - (27 if args.frames == "u8" else 0)) * H * W * S
     achieved = algo_bytes / (kern_pack_ms * 1e-3) / 1e9
-    tkey = (args.workload, args.noise, ems[0].resolved_engine)
+    tkey = (args.workload, args.noise, ems[0].resolved_engine) if args.frames == "f32" else None
     out = {
         "metric": "V2E+voxel Gpixel-frames/s", "value": round(value, 3), "unit": "Gpixel-frames/s",
         "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": round(ms_total / K, 5),
@@ -419,9 +425,9 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": f"{world} x independent sequence shard(s), no collective",
                    "cpu_binding": binding,
                    "emulator": EMU, "noise_mode": args.noise, "philox_rounds": args.philox_rounds,
-                   "engine": ems[0].resolved_engine, "frame_dtype": "f32", "voxel_dtype": "f32",
+                   "engine": ems[0].resolved_engine, "frame_dtype": args.frames, "voxel_dtype": "f32",
                    "l2_policy": f"inputs larger than L2: ring of {ring} distinct packs "
-                                f"({ring * pxf_step * 4 / 1e6:.0f} MB) per GPU"},
+                                f"({ring * pxf_step * fbytes / 1e6:.0f} MB) per GPU"},
         "e2e": {"value": round(e2e_value, 3), "unit": "Gpixel-frames/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "note": "EventEmulator.forward_host on f32 packs in pinned host memory: H2D copy "
@@ -540,6 +546,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--noise", default="philox", choices=["philox", "off"])
+    ap.add_argument("--frames", default="f32", choices=["f32", "u8"],
+                    help="dtype of the device-resident frames of `value` (f32: the reference contract)")
     ap.add_argument("--engine", default="auto", choices=["auto", "fixpoint", "persistent", "runahead", "stepwise"])
     ap.add_argument("--philox-rounds", type=int, default=10)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
