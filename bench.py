@@ -447,7 +447,7 @@ def run_ours(args, rank, world, local_rank):
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
                                        "ncu --set full capture (profiles/): bytes per pack x packs "
                                        "per launch",
-                     "peak_source": peak_src, "kernel": {"fixpoint": "k_fixpoint", "persistent": "k_persistent",
+                     "peak_source": peak_src, "kernel": {"fixpoint": "k_fixpoint_spec", "persistent": "k_persistent",
                                 "runahead": "k_runahead"}.get(ems[0].resolved_engine,
                                                               "k_phase_a/k_phase_b"),
                      "algorithmic_bytes_per_pack": algo_bytes,
