@@ -228,7 +228,7 @@ int v2e_batch_clip_forward(const v2e_config* c, const v2e_pack* packs, int n_pac
         workspace_bytes >= step_layout(cfg, n_seq).total &&
         v2e_resolve_engine(c, n_seq) == V2E_ENGINE_FIXPOINT) {
         const int rounds = c->philox_rounds == 7 ? 7 : 10;
-        int cap = 128 / n_seq;     // (kFxBlkSlots records per launch)
+        int cap = kFxBlkSlots / n_seq;     // (launch records per launch)
         if (cap > V2E_MAX_SEQ_PER_LAUNCH) cap = V2E_MAX_SEQ_PER_LAUNCH;
         while (cap > 1 && n_packs - i0 > 1) {
             const int m = n_packs - i0 < cap ? n_packs - i0 : cap;

@@ -13,6 +13,7 @@ constexpr size_t kTimelineBytes = 160 * 32 * 8 + 2048 + 1024;  // development ai
 // fixed-point engine: ring of launch records for multi-sequence launches (8 slots x 16 sequences
 // x (SeqDev + 32 FrameSc) <= 8 * 16 * 1280 bytes)
 constexpr size_t kFxBlkBytes = 8 * 16 * 1280;
+constexpr int kFxBlkSlots = 128;   // launch records (<= 1280 B each) the fixed-point engine's ring holds
 constexpr int kRaMaxTiles = 160;  // run-ahead engine: tiles (CTAs) per sequence, <= SM count
 
 // Per-sequence work area inside the caller's workspace.  Zero on entry, zero on exit.

@@ -50,7 +50,6 @@ struct FxSeqBlock {
 // launch records in the workspace: a circular buffer of kFxBlkSlots records; a launch takes
 // n_chain * n_seq consecutive ones (copied in stream order, so the copy for a launch never
 // overtakes the launch before it; consecutive launches use disjoint ranges whenever two fit)
-constexpr int kFxBlkSlots = 128;
 static_assert(sizeof(FxSeqBlock) <= 1280 && kFxBlkSlots * 1280 <= kFxBlkBytes,
               "workspace ring too small (v2e_engine.cuh, kFxBlkBytes)");
 
