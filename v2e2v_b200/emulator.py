@@ -328,11 +328,19 @@ class EventEmulator(nn.Module):
         return first
 
     def _get_scalar_prep(self, num_frames) -> PackScalarPrep:
+        # (the raw attribute values first: the float() conversions of the full key cost more than
+        # the C routine they feed)
+        raw = (num_frames, self.num_bins, self._refractory_host, self.cutoff_hz, self.ql, self.qs,
+               self.shot_noise_rate_hz)
+        prep = self.__dict__.get("_scalar_prep")
+        if prep is not None and prep.raw_key == raw:
+            return prep
         key = (num_frames, self.num_bins, float(self._refractory_host), float(self.cutoff_hz),
                float(self.ql), float(self.qs), float(self.shot_noise_rate_hz))
-        prep = getattr(self, "_scalar_prep", None)
         if prep is None or prep.key != key:
-            prep = self._scalar_prep = PackScalarPrep(*key)
+            prep = PackScalarPrep(*key)
+            object.__setattr__(self, "_scalar_prep", prep)
+        prep.raw_key = raw
         return prep
 
     def _prep_chunk_c(self, pk0, n, fptrs, rows, n_stamps, num_frames, height, width,
@@ -370,9 +378,11 @@ class EventEmulator(nn.Module):
                 self._first_pending = True
             return False
         self._t_prev.value, self._t_prev.is_f64 = tp.value, True
-        self.t_previous = tp.value
-        self.frame_counter += n * num_frames
-        self._pack_counter += n
+        # (plain attributes: written past nn.Module.__setattr__, which costs ~2.5 us a piece)
+        d = self.__dict__
+        d["t_previous"] = tp.value
+        d["frame_counter"] += n * num_frames
+        d["_pack_counter"] += n
         return True
 
     def _prep_pack(self, pk, fr, t_frames, vox_ptr, meta_ptr):

@@ -103,6 +103,7 @@ class PackScalarPrep:
                  ql: float, qs: float, shot_noise_rate_hz: float):
         self.key = (num_frames, num_bins, float(refractory_period_s), float(cutoff_hz), float(ql),
                     float(qs), float(shot_noise_rate_hz))
+        self.raw_key = None    # the caller's unconverted attribute values this key was built from
         hp = self.hp = _cabi.HostParams()
         hp.num_frames, hp.num_bins = num_frames, num_bins
         hp.cutoff_hz, hp.ql, hp.qs = float(cutoff_hz), float(ql), float(qs)
