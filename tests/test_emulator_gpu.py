@@ -196,7 +196,7 @@ def test_full_size_1280x720_properties():
         assert abs(v.mean().item()) < 1e-4 and abs(v.std(unbiased=False).item() - 1) < 1e-4
 
 
-@pytest.mark.parametrize("fdt", [torch.float32, torch.uint8])
+@pytest.mark.parametrize("fdt", [torch.float32, torch.uint8, torch.bfloat16])
 def test_forward_clip_equals_pack_loop(fdt):
     """forward_clip (one C call, K launches) == K calls of forward(): states, counts and voxel
     grids bit-identical (same Philox stream: the pack counter advances the same way)."""
@@ -345,7 +345,10 @@ def test_batch_forward_clip_equals_step_loop(S, shared):
     cfg, T, K = gc.CFG2, 10, 5
     H, W = (64, 96) if S > 16 else (260, 346)
     planes = [gc.make_planes(70 + s, H, W, cfg) for s in range(S)]
-    vids = [list(gc.video(90 + s, K, T, H, W)) for s in range(S)]
+    # (one row per sequence: every sequence on its own time base, so that a row taken from the
+    # wrong sequence shows)
+    vids = [list(gc.video(90 + s, K, T, H, W, fps=1000.0 if shared else 800.0 + 150.0 * s))
+            for s in range(S)]
     frames = [torch.cat([vids[s][k][1] for s in range(S)]).cuda() for k in range(K)]
     stamps = [vids[0][k][2] if shared else torch.cat([vids[s][k][2] for s in range(S)])
               for k in range(K)]
