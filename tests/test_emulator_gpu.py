@@ -286,7 +286,7 @@ def test_forward_clip_chained_launches(noise):
             torch.cuda.synchronize()
             nev = nev.tolist()
             launches = _cabi.lib().v2e_launch_count() - n0
-            assert launches <= 7, launches      # chunks of 1, 1, 2, 3, 5, 8, 4 packs
+            assert launches <= 3, launches      # chunks of 1, 16, 7 packs: one chain each
             spans = [ev[2 * j].elapsed_time(ev[2 * j + 1]) for j in range(K)]
             assert all(x >= 0 for x in spans)
             total = ev[0].elapsed_time(ev[2 * K - 1])
@@ -300,6 +300,34 @@ def test_forward_clip_chained_launches(noise):
     assert a[1] == b[1] and a[5] == b[5]
     for i in (0, 2, 3, 4):
         np.testing.assert_array_equal(a[i], b[i])
+
+
+def test_forward_clip_full_size_chain_vs_oracle():
+    """BASELINE configs[2] at full size through the bench's path: a clip of 4 packs of 1280x720
+    (launches of 1 + 3 chained packs) == the per-pack loop bit for bit, and the last pack's state
+    against the CPU oracle run on the kernel's own exported draws (per-pack emulator, debug maps)."""
+    cfg, H, W, T, K = gc.CFG2, 720, 1280, 10, 4
+    pos, neg, nra = gc.make_planes(41, H, W, cfg)
+    vids = [(fr, tfr) for _, fr, tfr in gc.video(21, K, T, H, W)]
+    em_c = gc.cuda_emulator(cfg, "auto", noise_mode="philox")
+    em_p = gc.cuda_emulator(cfg, "fixpoint", noise_mode="philox", debug_maps=True)
+    orc = OracleEmulator(**cfg, threads=0)
+    for e in (em_c, em_p, orc):
+        e.set_planes(pos, neg, nra)
+    em_c.philox_seed = em_p.philox_seed = 11
+    vox, nev = em_c.forward_clip([v[0].cuda() for v in vids], [v[1] for v in vids])
+    em_c.check_status()
+    nev = nev.tolist()
+    for k, (fr, tfr) in enumerate(vids):
+        v1, n1 = em_p(fr.cuda(), tfr)
+        d = em_p.last_debug
+        sh = gc.shot_rand_from_decisions(d["shot"].cpu().numpy(), d["pol"].cpu().numpy())
+        ov, onev = orc.forward(fr.numpy(), tfr, leak_randn=d["leak_randn"].cpu().numpy(), shot_rand=sh)
+        assert nev[k] == n1 == onev, k
+        np.testing.assert_array_equal(vox[k].cpu().numpy(), v1[0].cpu().numpy())
+        np.testing.assert_allclose(v1.cpu().numpy(), ov, rtol=VOX_RTOL, atol=VOX_ATOL)
+    gc.assert_state_equal(em_p, orc, True, "per-pack vs oracle")
+    gc.assert_state_equal(em_c, orc, True, "clip vs oracle")
 
 
 @pytest.mark.parametrize("engine", ["auto", "persistent", "stepwise"])
