@@ -6,7 +6,7 @@ import torch
 from tests import gpu_common as gc
 from v2e2v_b200 import EventEmulator
 
-H, W, T = 720, 1280, 10
+H, W, T = (int(v) for v in os.environ.get("V2E_PROBE_HWT", "720,1280,10").split(","))
 noise = sys.argv[1] if len(sys.argv) > 1 else "philox"
 engine = sys.argv[2] if len(sys.argv) > 2 else "auto"
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 50
