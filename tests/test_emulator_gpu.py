@@ -412,6 +412,47 @@ def test_batch_forward_clip_equals_step_loop(S, shared):
         np.testing.assert_array_equal(a[3][s], b[3][s])
 
 
+@pytest.mark.parametrize("fdt", [torch.float32, torch.uint8])
+def test_batch_forward_host_equals_forward(fdt):
+    """EventEmulatorBatch.forward_host (a step's frames in pinned host memory, staged on a copy
+    stream, frame 0 of steady-state packs not copied) == forward on device frames, bit for bit."""
+    from v2e2v_b200 import EventEmulatorBatch
+    cfg, H, W, T, S, K = gc.CFG2, 64, 96, 10, 5, 4
+    planes = [gc.make_planes(50 + s, H, W, cfg) for s in range(S)]
+    vids = [list(gc.video(70 + s, K, T, H, W)) for s in range(S)]
+    res = []
+    for host in (False, True):
+        batch = EventEmulatorBatch(S, device="cuda", noise_mode="philox", **cfg)
+        for s in range(S):
+            batch[s].philox_seed = 300 + s
+            batch[s].set_planes(*planes[s])
+        outs = []
+        for k in range(K):
+            fr = torch.cat([vids[s][k][1] for s in range(S)]).to(fdt)
+            tf = torch.cat([vids[s][k][2] for s in range(S)])
+            if host:
+                fr = fr.pin_memory()
+                fr_keep = fr.clone()
+                v, n = batch.forward_host(fr, tf)
+                if k:
+                    fr[:, 0] = 255 - fr[:, 0]     # frame 0 of a steady-state pack is never read
+                torch.cuda.synchronize()
+                del fr_keep
+            else:
+                v, n = batch(fr.cuda(), tf)
+            outs.append((v.cpu().numpy(), n.cpu().numpy()))
+        batch.check_status()
+        res.append((outs, [batch[s].base_log_frame.cpu().numpy() for s in range(S)],
+                    [batch[s].timestamp_mem.cpu().numpy() for s in range(S)]))
+    a, b = res
+    for k in range(K):
+        np.testing.assert_array_equal(a[0][k][1], b[0][k][1])
+        np.testing.assert_array_equal(a[0][k][0], b[0][k][0])
+    for s in range(S):
+        np.testing.assert_array_equal(a[1][s], b[1][s])
+        np.testing.assert_array_equal(a[2][s], b[2][s])
+
+
 def test_batch_full_size_64_sequences():
     """BASELINE configs[3] at full size: 64 sequences of 346x260 in one EventEmulatorBatch (four
     launch groups of 16), two steps through forward_clip.  Sampled sequences == separate

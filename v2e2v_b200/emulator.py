@@ -921,6 +921,49 @@ class EventEmulatorBatch(nn.Module):
         num_events = meta[:, :, 0:2].contiguous().view(torch.int64).reshape(K, S)
         return out, num_events
 
+    def forward_host(self, frames, t_frames):
+        """``forward`` for a step whose frames live in HOST memory (extension, the batch's
+        counterpart of `EventEmulator.forward_host`): frames is a CPU tensor [S, T, H, W] (ideally
+        pinned), staged through two device buffers on a copy stream so that the copy of step k+1
+        runs while the kernels of step k do.  Frame 0 of a pack is read only by a sequence in its
+        first pack after `reset()` (v2e_model.py:263,350,325-327): when no sequence is, the T-1
+        other frames of every sequence cross the bus.  Returns what `forward` returns."""
+        if frames.is_cuda:
+            return self.forward(frames, t_frames)
+        S = len(self.emulators)
+        if frames.dim() != 4 or frames.size(0) != S:
+            raise ValueError("frames must be [n_sequences, num_frames, height, width]")
+        if frames.dtype not in ops._FRAME_DT:
+            frames = frames.float()
+        dev = self.emulators[0]._dev
+        st = getattr(self, "_host_stage", None)
+        if st is None or st["shape"] != tuple(frames.shape) or st["dtype"] != frames.dtype:
+            st = self._host_stage = {
+                "shape": tuple(frames.shape), "dtype": frames.dtype, "k": 0,
+                "buf": [torch.empty(frames.shape, dtype=frames.dtype, device=dev) for _ in range(2)],
+                "ready": [torch.cuda.Event() for _ in range(2)],
+                "freed": [torch.cuda.Event() for _ in range(2)],
+                "stream": torch.cuda.Stream(dev)}
+        b = st["k"] & 1
+        st["k"] += 1
+        lo = 0 if any(em.base_log_frame is None for em in self.emulators) else 1
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(st["stream"]):
+            st["stream"].wait_event(st["freed"][b])
+            if lo == 0:
+                st["buf"][b].copy_(frames, non_blocking=True)
+            else:
+                # (one contiguous copy per sequence: a strided [S, T-1, H, W] copy_ from pinned
+                # memory goes through a synchronous staging path in torch)
+                buf = st["buf"][b]
+                for i in range(S):
+                    buf[i, lo:].copy_(frames[i, lo:], non_blocking=True)
+            st["ready"][b].record(st["stream"])
+        cur.wait_event(st["ready"][b])
+        out = self.forward(st["buf"][b], t_frames)
+        st["freed"][b].record(cur)
+        return out
+
     def forward(self, frames, t_frames):
         S = len(self.emulators)
         if isinstance(frames, torch.Tensor):
