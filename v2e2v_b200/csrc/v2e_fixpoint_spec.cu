@@ -1373,10 +1373,42 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
         }
     }
     __syncthreads();
-    {
+    // ---- leave the barrier words zeroed: the last CTA of the sequence to report cleans up ----------
+    // The CTA is done with this pack's barrier words: warp 0 reports that (and cleans up if the
+    // CTA is the sequence's last to get here) while the other warps commit - the atomic's round
+    // trip is off the path every pack ends with.  (Warp 0: its lane 0 is the thread that arrives
+    // at the grid barriers of the next pack, so its fence after the clean-up orders the zeroed
+    // words before that arrival.)
+    constexpr int kCommitThreads = kSpThreads - 32;
+    const int ctid = tid - 32;
+    if (warp == 0) {
+        unsigned last = 0;
+        if (lane == 0) {
+            __threadfence();
+            last = atomicAdd(&fx.exit_count, 1u) == (unsigned)prm.tiles_per_seq - 1u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            const int used = min(pass + 1, kFxMaxRounds);
+            for (int i = lane; i < used * V2E_MAX_FRAMES; i += 32) (&fx.gmax[0][0])[i] = 0u;
+            for (int i = lane; i < used * 8; i += 32) (&fx.stat[0][0])[i] = 0ull;
+            for (int i = lane; i < kSpPre * kRaMaxTiles; i += 32) (&fx.hint[0][0])[i] = 0ull;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                fx.exit_count = 0;
+                fx.arrive = 0;
+                if (prm.timeline && seq == 0) {
+                    prm.timeline[160 * 32 + 2 * (fx0.pad[0] & 127u) + 1] = fx_now();
+                    prm.timeline[160 * 32 + 256 + (fx0.pad[0] & 127u)] = pass + 1;   // rounds, pre-pass included
+                    fx0.pad[0] += 1;
+                }
+            }
+        }
+    } else {
         const float mean = s_stat[0], den = s_stat[1];
         const bool norm = s_stat[2] != 0.f;
-        for (int i = tid; i < n_ent; i += kSpThreads) {
+        for (int i = ctid; i < n_ent; i += kCommitThreads) {
             const unsigned* ep = s_ent + i;
             const unsigned meta = ep[FX_META * cap];
             const int p = tile_px0 + (int)ep[FX_IDX * cap];
@@ -1414,7 +1446,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
                 }
             }
         }
-        for (int e = tid; e < n_spill; e += kSpThreads) {
+        for (int e = ctid; e < n_spill; e += kCommitThreads) {
             const int p = tile_px0 + (int)spill_list[e];
             sq.base[p] = spill_state[p];
             if (CUTOFF) sq.lp[p] = spill_state[(size_t)P + p];
@@ -1430,29 +1462,6 @@ __global__ void __launch_bounds__(kSpThreads, 1) k_fixpoint_spec(const __grid_co
     if (tl && pk == min(2, prm.n_chain - 1)) {   // (a chain reports its third pack: one in steady state)
         __syncthreads();
         if (tid < 32) tl_out[tid] = tl[tid];
-    }
-    // ---- leave the barrier words zeroed: the last CTA of the sequence to get here cleans up ----------
-    if (tid == 0) {
-        __threadfence();
-        s_cnt[0] = atomicAdd(&fx.exit_count, 1u) == (unsigned)prm.tiles_per_seq - 1u;
-    }
-    __syncthreads();
-    if (s_cnt[0]) {
-        const int used = min(pass + 1, kFxMaxRounds);
-        for (int i = tid; i < used * V2E_MAX_FRAMES; i += kSpThreads) (&fx.gmax[0][0])[i] = 0u;
-        for (int i = tid; i < used * 8; i += kSpThreads) (&fx.stat[0][0])[i] = 0ull;
-        for (int i = tid; i < kSpPre * kRaMaxTiles; i += kSpThreads) (&fx.hint[0][0])[i] = 0ull;
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            fx.exit_count = 0;
-            fx.arrive = 0;
-            if (prm.timeline && seq == 0) {
-                prm.timeline[160 * 32 + 2 * (fx0.pad[0] & 127u) + 1] = fx_now();
-                prm.timeline[160 * 32 + 256 + (fx0.pad[0] & 127u)] = pass + 1;   // rounds, pre-pass included
-                fx0.pad[0] += 1;
-            }
-        }
     }
     __syncthreads();   // (the next pack of the chain re-initialises the header)
     }
