@@ -56,10 +56,10 @@ EMU = dict(output_mode="voxel_grid", num_bins=5, pos_thres=0.6, neg_thres=0.6, s
            pl=1.5, ps=0.5, ql=1, qs=0, cutoff_hz=200)     # cfg2 params + model_v2e2v.py:56-57
 ALGO_BYTES_PER_PIXEL_PACK = 92      # 9 f32 frames + 5 f32 bins + 6 planes in + 3 planes out
 # measured DRAM bytes per PACK (ncu --set full: profiles/r02_k_fixpoint_spec_chain16_* for the
-# fixed-point engine - a chained launch of 16 packs, 600.6 MB read + 305.7 MB written; profiles/r01_*
+# fixed-point engine - a chained launch of 16 packs, 615.1 MB read + 308.2 MB written; profiles/r01_*
 # for the others): (workload, noise, engine)
 TRAFFIC_BYTES = {("cfg3", "philox", "persistent"): 55447040 + 3553024,
-                 ("cfg3", "philox", "fixpoint"): (600577024 + 305681920) // 16,
+                 ("cfg3", "philox", "fixpoint"): (615143936 + 308164352) // 16,
                  ("cfg3", "off", "fixpoint"): 51731968 + 3537152}
 
 
